@@ -1,0 +1,613 @@
+// cp_api.cu — kernels and the C ABI of libcpgpu.so (see include/cp_gpu.h).
+//
+// Built for sm_100a only, with -fmad=false (no contraction: see cp_device.cuh).  There is no CPU
+// path in this library: every compute entry point launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "cp_device.cuh"
+#include "cp_internal.h"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+cp_status cp_fail(cp_status st, const char *msg) {
+    g_last_error = msg ? msg : "";
+    return st;
+}
+
+static cp_status cuda_fail(cudaError_t e, const char *what) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    return cp_fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? CP_ERR_NO_DEVICE : CP_ERR_CUDA, buf);
+}
+
+#define CP_CUDA(call)                                         \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ kernels
+constexpr int kBlock = 128;
+
+struct SharedLayout {
+    int items_off, shift_off, group_off, group_stride, img_doubles;
+    size_t bytes;
+};
+
+__host__ __device__ inline SharedLayout shared_layout(int kind, int n_items, int n_syms, int lanes) {
+    SharedLayout s;
+    const int cw = kind == CP_POLYGON ? 8 : 4;
+    s.items_off = 0;
+    s.shift_off = n_items * 5;
+    s.group_off = s.shift_off + n_items;
+    s.img_doubles = n_syms * 8;
+    s.group_stride = s.img_doubles + n_syms * n_items * cw;
+    s.bytes = sizeof(double) * (size_t)(s.group_off + (kBlock / lanes) * s.group_stride);
+    return s;
+}
+
+template <int KIND, int L>
+__device__ __forceinline__ Geo stage_shared(const KProblem &P, double *smem, const double *&s_items,
+                                            const double *&s_shift) {
+    const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
+    for (int i = threadIdx.x; i < P.n_items * 5; i += kBlock) smem[lay.items_off + i] = P.items[i / 5][i % 5];
+    for (int i = threadIdx.x; i < P.n_items; i += kBlock) smem[lay.shift_off + i] = P.lj_shift[i];
+    __syncthreads();
+    s_items = smem + lay.items_off;
+    s_shift = smem + lay.shift_off;
+    Geo g;
+    g.img = smem + lay.group_off + (threadIdx.x / L) * lay.group_stride;
+    g.comp = g.img + lay.img_doubles;
+    return g;
+}
+
+// The Monte-Carlo optimisation of one replica per group: every stage of MCOptimiser::optimise_state
+// (optimisation.rs:80-180) chained as analyse_state does (main.rs:224-252), annealing schedule,
+// step-size adaptation and convergence counter on the device.
+template <int KIND, int L, int RNG>
+__global__ void __launch_bounds__(kBlock) mc_kernel(const __grid_constant__ KParams K) {
+    extern __shared__ double smem[];
+    const KProblem &P = K.prob;
+    const double *s_items, *s_shift;
+    Geo g = stage_shared<KIND, L>(P, smem, s_items, s_shift);
+    const int lane = threadIdx.x % L;
+    const unsigned gmask = group_mask<L>();
+    const unsigned long long rep = (unsigned long long)blockIdx.x * (kBlock / L) + threadIdx.x / L;
+    if (rep >= K.n_replicas) return;
+    const unsigned long long replica = K.replica_begin + rep;
+
+    Dof d;
+#pragma unroll
+    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = K.init_dof ? K.init_dof[rep * CP_MAX_DOF + i] : P.dof[i];
+
+    const int n_cell = n_cell_dof(P.family);
+    const int n_basis = n_cell + 3;
+    unsigned long long rejections = 0, moves = 0;
+    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+    bool valid = score_current == score_current;
+    if (!valid && lane == 0) atomicExch(K.error_flag, 1);  // panic!("Invalid configuration ...")
+
+    Rng rng;
+    for (int stage = 0; valid && stage < K.n_stages; ++stage) {
+        const KStage S = K.stages[stage];
+        // generate_basis(): the upper bounds of length and ratio are their values now (cell.rs:139-152)
+        const double len0 = d.v[0], ratio0 = d.v[1];
+        rng_begin_stage<RNG>(rng, K.seed_base + replica, replica, n_basis);
+        double kt = S.kt_start, step_ratio = 1.0;
+        int convergence_count = 0;
+        const unsigned long long outer = S.inner ? S.steps / S.inner : 0ull;
+        bool converged = false;
+        for (unsigned long long loop = 1; loop <= outer && !converged; ++loop) {
+            const double score_start = score_current;
+            unsigned long long loop_rejections = 0;
+            for (unsigned long long it = 0; it < S.inner; ++it) {
+                int basis_index;
+                double sample;
+                rng_draw_move<RNG>(rng, basis_index, sample);
+                const int slot = basis_to_slot(basis_index, n_cell);
+                const double val = d.get(slot);
+                const double new_val = val + S.max_step * step_ratio * sample;  // optimisation.rs:115-119
+                double lo, hi;
+                slot_bounds(slot, len0, ratio0, lo, hi);
+                if (!(lo <= new_val && new_val <= hi)) {  // Basis::set_value Err (basis/mod.rs:31-35)
+                    ++loop_rejections;
+                    continue;
+                }
+                d.set(slot, new_val);
+                const double new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+                const double threshold = rng_draw_threshold<RNG>(rng);
+                if (accept_move(new_score, score_current, kt, threshold)) {
+                    score_current = new_score;
+                } else {
+                    d.set(slot, val);
+                    ++loop_rejections;
+                }
+            }
+            moves += S.inner;
+            rejections += loop_rejections;
+            kt *= S.kt_ratio;
+            if (S.convergence == S.convergence) {  // Some(precision) (optimisation.rs:142-159)
+                if (score_current - score_start < S.convergence) {
+                    if (++convergence_count > 5) converged = true;
+                } else {
+                    convergence_count = 0;
+                }
+            }
+            if (!converged && step_ratio > 1e-4)  // optimisation.rs:165-167
+                step_ratio *= (double)S.inner / ((double)loop_rejections + 1.);
+        }
+    }
+    if (lane == 0) {
+        cp_replica_result r;
+#pragma unroll
+        for (int i = 0; i < CP_MAX_DOF; ++i) r.dof[i] = d.v[i];
+        r.score = score_current;
+        r.rejections = rejections;
+        r.moves = moves;
+        K.out[rep] = r;
+    }
+}
+
+template <int KIND, int L>
+__global__ void __launch_bounds__(kBlock)
+score_kernel(const __grid_constant__ KProblem P, const double *dof, unsigned long long n, double *out) {
+    extern __shared__ double smem[];
+    const double *s_items, *s_shift;
+    Geo g = stage_shared<KIND, L>(P, smem, s_items, s_shift);
+    const int lane = threadIdx.x % L;
+    const unsigned gmask = group_mask<L>();
+    const unsigned long long rep = (unsigned long long)blockIdx.x * (kBlock / L) + threadIdx.x / L;
+    if (rep >= n) return;
+    Dof d;
+#pragma unroll
+    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = dof[rep * CP_MAX_DOF + i];
+    double s = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+    if (lane == 0) out[rep] = s;
+}
+
+// the inner-loop body optimisation.rs:104-136 driven by recorded draws
+template <int KIND, int L>
+__global__ void __launch_bounds__(kBlock)
+replay_kernel(const __grid_constant__ KProblem P, const double *init_dof, const cp_move *mv,
+              unsigned long long n_moves, unsigned long long n, cp_decision *out) {
+    extern __shared__ double smem[];
+    const double *s_items, *s_shift;
+    Geo g = stage_shared<KIND, L>(P, smem, s_items, s_shift);
+    const int lane = threadIdx.x % L;
+    const unsigned gmask = group_mask<L>();
+    const unsigned long long rep = (unsigned long long)blockIdx.x * (kBlock / L) + threadIdx.x / L;
+    if (rep >= n) return;
+    Dof d;
+#pragma unroll
+    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = init_dof[rep * CP_MAX_DOF + i];
+    const int n_cell = n_cell_dof(P.family);
+    const double len0 = d.v[0], ratio0 = d.v[1];
+    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+    for (unsigned long long m = 0; m < n_moves; ++m) {
+        const cp_move M = mv[rep * n_moves + m];
+        const int slot = basis_to_slot((int)M.basis_index, n_cell);
+        const double val = d.get(slot);
+        double lo, hi;
+        slot_bounds(slot, len0, ratio0, lo, hi);
+        cp_decision D;
+        D.in_bounds = 0;
+        D.accepted = 0;
+        D.new_score = __longlong_as_double(0x7FF8000000000000ll);
+        if (lo <= M.new_value && M.new_value <= hi) {
+            D.in_bounds = 1;
+            d.set(slot, M.new_value);
+            D.new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+            if (accept_move(D.new_score, score_current, M.kt, M.threshold)) {
+                score_current = D.new_score;
+                D.accepted = 1;
+            } else {
+                d.set(slot, val);
+            }
+        }
+        D.score_current = score_current;
+        if (lane == 0) out[rep * n_moves + m] = D;
+    }
+}
+
+// .max() over replicas ordered by score (main.rs:253, packed.rs:49-68); ties keep the lowest index
+struct BestKey {
+    double score;
+    unsigned long long index;
+};
+__device__ __forceinline__ bool better(const BestKey &a, const BestKey &b) {
+    // is a better than b?  NaN (None) never wins
+    if (!(a.score == a.score)) return false;
+    if (!(b.score == b.score)) return true;
+    return a.score > b.score || (a.score == b.score && a.index < b.index);
+}
+__global__ void __launch_bounds__(256)
+best_kernel(const cp_replica_result *res, const BestKey *partial_in, unsigned long long n, BestKey *out) {
+    __shared__ BestKey sh[256];
+    BestKey best{__longlong_as_double(0x7FF8000000000000ll), ~0ull};
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        BestKey c = partial_in ? partial_in[i] : BestKey{res[i].score, i};
+        if (better(c, best)) best = c;
+    }
+    sh[threadIdx.x] = best;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s && better(sh[threadIdx.x + s], sh[threadIdx.x])) sh[threadIdx.x] = sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------ context
+struct cp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[7] = {};  // h2d 0-1, mc 2-3, reduce end 4, d2h 5-6
+    int lanes = 0;  // 0 = automatic
+    // prepared job
+    bool prepared = false, launched = false;
+    KParams params{};
+    cp_replica_result *d_out = nullptr;
+    double *d_init = nullptr;
+    BestKey *d_partial = nullptr;  // [kPartials + 1]
+    int *d_error = nullptr;
+    size_t cap_out = 0, cap_init = 0;
+    cp_timing timing{};
+    bool timed_h2d = false;
+};
+constexpr int kPartials = 592;  // 148 SMs x 4
+
+static double powi6_host(double x) { double x2 = x * x, x4 = x2 * x2; return x2 * x4; }
+static double powi12_host(double x) { double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4; return x4 * x8; }
+
+static cp_status make_kproblem(const cp_problem *p, KProblem *k) {
+    if (!p) return cp_fail(CP_ERR_INVALID_ARG, "null problem");
+    if (p->kind < CP_POLYGON || p->kind > CP_LJ) return cp_fail(CP_ERR_INVALID_ARG, "problem.kind out of range");
+    if (p->n_items < 1 || p->n_items > CP_MAX_ITEMS) return cp_fail(CP_ERR_INVALID_ARG, "problem.n_items out of range");
+    if (p->n_syms < 1 || p->n_syms > CP_MAX_SYMS) return cp_fail(CP_ERR_INVALID_ARG, "problem.n_syms out of range");
+    if (p->family < CP_MONOCLINIC || p->family > CP_TETRAGONAL) return cp_fail(CP_ERR_INVALID_ARG, "problem.family out of range");
+    std::memset(k, 0, sizeof *k);
+    k->kind = p->kind;
+    k->n_items = p->n_items;
+    k->family = p->family;
+    k->n_syms = p->n_syms;
+    std::memcpy(k->items, p->items, sizeof k->items);
+    std::memcpy(k->syms, p->syms, sizeof k->syms);
+    std::memcpy(k->dof, p->dof, sizeof k->dof);
+    k->area = p->area;
+    k->radius = p->enclosing_radius;
+    if (p->kind == CP_LJ)
+        for (int i = 0; i < p->n_items; ++i) {
+            const double sigma = p->items[i][2], eps = p->items[i][3], x = p->items[i][4];
+            // lj2.rs:50-51: 4. * epsilon * ((sigma / x).powi(12) - (sigma / x).powi(6))
+            k->lj_shift[i] = std::isnan(x) ? 0. : 4. * eps * (powi12_host(sigma / x) - powi6_host(sigma / x));
+        }
+    return CP_OK;
+}
+
+static int auto_lanes(const KProblem &k) {
+    // lanes per replica: enough parallel work per move to keep the lanes busy
+    const int pair_tests = k.n_syms * (k.n_syms - 1) / 2 * k.n_items * k.n_items;
+    const int cands = k.n_syms * k.n_syms * (k.kind == CP_LJ ? 48 : 8);
+    const int work = pair_tests > cands ? pair_tests : cands;
+    if (work >= 32) return 32;
+    if (work >= 16) return 16;
+    return 8;
+}
+
+template <int KIND, int L>
+static cudaError_t launch_mc(const KParams &K, cudaStream_t st) {
+    const SharedLayout lay = shared_layout(KIND, K.prob.n_items, K.prob.n_syms, L);
+    const unsigned long long gpb = kBlock / L;
+    const unsigned grid = (unsigned)((K.n_replicas + gpb - 1) / gpb);
+    if (K.rng_mode == CP_RNG_PCG64MCG)
+        mc_kernel<KIND, L, CP_RNG_PCG64MCG><<<grid, kBlock, lay.bytes, st>>>(K);
+    else
+        mc_kernel<KIND, L, CP_RNG_PHILOX><<<grid, kBlock, lay.bytes, st>>>(K);
+    return cudaGetLastError();
+}
+
+#define CP_DISPATCH(FN, kind, lanes, ...)                                           \
+    [&]() -> cudaError_t {                                                          \
+        switch ((kind) * 100 + (lanes)) {                                           \
+        case CP_POLYGON * 100 + 4: return FN<CP_POLYGON, 4>(__VA_ARGS__);           \
+        case CP_POLYGON * 100 + 8: return FN<CP_POLYGON, 8>(__VA_ARGS__);           \
+        case CP_POLYGON * 100 + 16: return FN<CP_POLYGON, 16>(__VA_ARGS__);         \
+        case CP_POLYGON * 100 + 32: return FN<CP_POLYGON, 32>(__VA_ARGS__);         \
+        case CP_DISCS * 100 + 4: return FN<CP_DISCS, 4>(__VA_ARGS__);               \
+        case CP_DISCS * 100 + 8: return FN<CP_DISCS, 8>(__VA_ARGS__);               \
+        case CP_DISCS * 100 + 16: return FN<CP_DISCS, 16>(__VA_ARGS__);             \
+        case CP_DISCS * 100 + 32: return FN<CP_DISCS, 32>(__VA_ARGS__);             \
+        case CP_LJ * 100 + 4: return FN<CP_LJ, 4>(__VA_ARGS__);                     \
+        case CP_LJ * 100 + 8: return FN<CP_LJ, 8>(__VA_ARGS__);                     \
+        case CP_LJ * 100 + 16: return FN<CP_LJ, 16>(__VA_ARGS__);                   \
+        case CP_LJ * 100 + 32: return FN<CP_LJ, 32>(__VA_ARGS__);                   \
+        default: return cudaErrorInvalidValue;                                      \
+        }                                                                           \
+    }()
+
+template <int KIND, int L>
+static cudaError_t launch_score(const KProblem &P, const double *dof, unsigned long long n, double *out,
+                                cudaStream_t st) {
+    const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
+    const unsigned long long gpb = kBlock / L;
+    score_kernel<KIND, L><<<(unsigned)((n + gpb - 1) / gpb), kBlock, lay.bytes, st>>>(P, dof, n, out);
+    return cudaGetLastError();
+}
+
+template <int KIND, int L>
+static cudaError_t launch_replay(const KProblem &P, const double *init, const cp_move *mv,
+                                 unsigned long long n_moves, unsigned long long n, cp_decision *out,
+                                 cudaStream_t st) {
+    const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
+    const unsigned long long gpb = kBlock / L;
+    replay_kernel<KIND, L><<<(unsigned)((n + gpb - 1) / gpb), kBlock, lay.bytes, st>>>(P, init, mv, n_moves, n, out);
+    return cudaGetLastError();
+}
+
+static int effective_lanes(const cp_ctx *ctx, const KProblem &k) { return ctx->lanes ? ctx->lanes : auto_lanes(k); }
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *cp_last_error(void) { return g_last_error.c_str(); }
+const char *cp_version(void) { return "crystal-packing_b200 0.1 (sm_100a)"; }
+
+cp_status cp_device_count(int *out) {
+    if (!out) return cp_fail(CP_ERR_INVALID_ARG, "cp_device_count: null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out = 0;
+        return cuda_fail(e, "cudaGetDeviceCount");
+    }
+    *out = n;
+    return CP_OK;
+}
+
+cp_status cp_init(int device, cp_ctx **out) {
+    if (!out) return cp_fail(CP_ERR_INVALID_ARG, "cp_init: null output");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (n == 0) return cp_fail(CP_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (device < 0 || device >= n) return cp_fail(CP_ERR_INVALID_ARG, "cp_init: device index out of range");
+    CP_CUDA(cudaSetDevice(device));
+    cp_ctx *ctx = new (std::nothrow) cp_ctx();
+    if (!ctx) return cp_fail(CP_ERR_CUDA, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CP_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CP_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto &ev : ctx->ev) CP_CUDA(cudaEventCreate(&ev));
+    CP_CUDA(cudaMalloc(&ctx->d_partial, sizeof(BestKey) * (kPartials + 1)));
+    CP_CUDA(cudaMalloc(&ctx->d_error, sizeof(int)));
+    *out = ctx;
+    return CP_OK;
+}
+
+void cp_destroy(cp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_out);
+    cudaFree(ctx->d_init);
+    cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_error);
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+cp_status cp_set_stream(cp_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_set_stream: null ctx");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return CP_OK;
+}
+
+cp_status cp_set_lanes(cp_ctx *ctx, int lanes) {
+    if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_set_lanes: null ctx");
+    if (lanes != 0 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return cp_fail(CP_ERR_INVALID_ARG, "cp_set_lanes: lanes must be 0, 4, 8, 16 or 32");
+    ctx->lanes = lanes;
+    return CP_OK;
+}
+
+cp_status cp_prepare(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stages, int n_stages,
+                     int rng_mode, uint64_t seed_base, uint64_t replica_begin, uint64_t n_replicas,
+                     const double *init_dof) {
+    if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_prepare: null ctx");
+    if (!stages || n_stages < 1 || n_stages > CP_MAX_STAGES)
+        return cp_fail(CP_ERR_INVALID_ARG, "cp_prepare: n_stages must be 1..CP_MAX_STAGES");
+    if (rng_mode != CP_RNG_PCG64MCG && rng_mode != CP_RNG_PHILOX)
+        return cp_fail(CP_ERR_INVALID_ARG, "cp_prepare: unknown rng_mode");
+    if (n_replicas == 0) return cp_fail(CP_ERR_INVALID_ARG, "cp_prepare: n_replicas must be > 0");
+    ctx->prepared = false;
+    KParams &K = ctx->params;
+    cp_status st = make_kproblem(problem, &K.prob);
+    if (st != CP_OK) return st;
+    for (int s = 0; s < n_stages; ++s) {
+        K.stages[s].kt_start = stages[s].kt_start;
+        K.stages[s].kt_ratio = stages[s].kt_ratio;
+        K.stages[s].max_step = stages[s].max_step_size;
+        K.stages[s].steps = stages[s].steps;
+        K.stages[s].inner = stages[s].inner_steps;
+        K.stages[s].convergence = stages[s].convergence;
+    }
+    K.n_stages = n_stages;
+    K.rng_mode = rng_mode;
+    K.seed_base = seed_base;
+    K.replica_begin = replica_begin;
+    K.n_replicas = n_replicas;
+    CP_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->cap_out < n_replicas) {
+        cudaFree(ctx->d_out);
+        ctx->d_out = nullptr;
+        ctx->cap_out = 0;
+        CP_CUDA(cudaMalloc(&ctx->d_out, sizeof(cp_replica_result) * n_replicas));
+        ctx->cap_out = n_replicas;
+    }
+    K.out = ctx->d_out;
+    K.error_flag = ctx->d_error;
+    K.init_dof = nullptr;
+    ctx->timed_h2d = false;
+    if (init_dof) {
+        if (ctx->cap_init < n_replicas) {
+            cudaFree(ctx->d_init);
+            ctx->d_init = nullptr;
+            ctx->cap_init = 0;
+            CP_CUDA(cudaMalloc(&ctx->d_init, sizeof(double) * CP_MAX_DOF * n_replicas));
+            ctx->cap_init = n_replicas;
+        }
+        CP_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CP_CUDA(cudaMemcpyAsync(ctx->d_init, init_dof, sizeof(double) * CP_MAX_DOF * n_replicas,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        CP_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        K.init_dof = ctx->d_init;
+        ctx->timed_h2d = true;
+    }
+    ctx->prepared = true;
+    ctx->launched = false;
+    return CP_OK;
+}
+
+cp_status cp_launch(cp_ctx *ctx) {
+    if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_launch: null ctx");
+    if (!ctx->prepared) return cp_fail(CP_ERR_NOT_PREPARED, "cp_launch: call cp_prepare first");
+    CP_CUDA(cudaSetDevice(ctx->device));
+    const KParams &K = ctx->params;
+    const int lanes = effective_lanes(ctx, K.prob);
+    CP_CUDA(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
+    CP_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CP_CUDA(CP_DISPATCH(launch_mc, K.prob.kind, lanes, K, ctx->stream));
+    CP_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    best_kernel<<<kPartials, 256, 0, ctx->stream>>>(ctx->d_out, nullptr, K.n_replicas, ctx->d_partial);
+    CP_CUDA(cudaGetLastError());
+    best_kernel<<<1, 256, 0, ctx->stream>>>(nullptr, ctx->d_partial, kPartials, ctx->d_partial + kPartials);
+    CP_CUDA(cudaGetLastError());
+    CP_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    ctx->timing.launches = 3;
+    ctx->timing.lanes_per_replica = (uint32_t)lanes;
+    ctx->launched = true;
+    return CP_OK;
+}
+
+cp_status cp_synchronize(cp_ctx *ctx) {
+    if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_synchronize: null ctx");
+    CP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CP_OK;
+}
+
+cp_status cp_fetch(cp_ctx *ctx, cp_best *out_best, cp_replica_result *out_all) {
+    if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_fetch: null ctx");
+    if (!ctx->launched) return cp_fail(CP_ERR_NOT_PREPARED, "cp_fetch: nothing was launched");
+    CP_CUDA(cudaSetDevice(ctx->device));
+    const KParams &K = ctx->params;
+    BestKey key{};
+    int err = 0;
+    CP_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    if (out_all)
+        CP_CUDA(cudaMemcpyAsync(out_all, ctx->d_out, sizeof(cp_replica_result) * K.n_replicas,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    CP_CUDA(cudaMemcpyAsync(&key, ctx->d_partial + kPartials, sizeof key, cudaMemcpyDeviceToHost, ctx->stream));
+    CP_CUDA(cudaMemcpyAsync(&err, ctx->d_error, sizeof err, cudaMemcpyDeviceToHost, ctx->stream));
+    CP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    CP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_best) {
+        std::memset(out_best, 0, sizeof *out_best);
+        out_best->result.score = std::nan("");
+        out_best->replica = ~0ull;
+        if (key.index != ~0ull) {
+            CP_CUDA(cudaMemcpy(&out_best->result, ctx->d_out + key.index, sizeof(cp_replica_result),
+                               cudaMemcpyDeviceToHost));
+            out_best->replica = K.replica_begin + key.index;
+        }
+    }
+    float ms = 0.f;
+    ctx->timing.h2d_ms = 0.f;
+    if (ctx->timed_h2d && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timing.h2d_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->timing.kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) ctx->timing.reduce_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ctx->timing.d2h_ms = ms;
+    if (err) return cp_fail(CP_ERR_INVALID_STATE, "Invalid configuration passed to function, exiting.");
+    return CP_OK;
+}
+
+cp_status cp_last_timing(cp_ctx *ctx, cp_timing *out) {
+    if (!ctx || !out) return cp_fail(CP_ERR_INVALID_ARG, "cp_last_timing: null argument");
+    *out = ctx->timing;
+    return CP_OK;
+}
+
+cp_status cp_run(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stages, int n_stages,
+                 int rng_mode, uint64_t seed_base, uint64_t replica_begin, uint64_t n_replicas,
+                 const double *init_dof, cp_best *out_best, cp_replica_result *out_all) {
+    cp_status st = cp_prepare(ctx, problem, stages, n_stages, rng_mode, seed_base, replica_begin, n_replicas, init_dof);
+    if (st == CP_OK) st = cp_launch(ctx);
+    if (st == CP_OK) st = cp_fetch(ctx, out_best, out_all);
+    return st;
+}
+
+cp_status cp_score(cp_ctx *ctx, const cp_problem *problem, const double *dof, uint64_t n, double *out_scores) {
+    if (!ctx || !dof || !out_scores) return cp_fail(CP_ERR_INVALID_ARG, "cp_score: null argument");
+    if (n == 0) return CP_OK;
+    KProblem kp;
+    cp_status st = make_kproblem(problem, &kp);
+    if (st != CP_OK) return st;
+    CP_CUDA(cudaSetDevice(ctx->device));
+    double *d_dof = nullptr, *d_out = nullptr;
+    CP_CUDA(cudaMalloc(&d_dof, sizeof(double) * CP_MAX_DOF * n));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_dof, dof, sizeof(double) * CP_MAX_DOF * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = CP_DISPATCH(launch_score, kp.kind, effective_lanes(ctx, kp), kp, d_dof, n, d_out, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_dof);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "cp_score");
+    return CP_OK;
+}
+
+cp_status cp_replay(cp_ctx *ctx, const cp_problem *problem, const double *init_dof, const cp_move *moves,
+                    uint64_t n_moves, uint64_t n_replicas, cp_decision *out) {
+    if (!ctx || !init_dof || !moves || !out) return cp_fail(CP_ERR_INVALID_ARG, "cp_replay: null argument");
+    if (n_moves == 0 || n_replicas == 0) return CP_OK;
+    KProblem kp;
+    cp_status st = make_kproblem(problem, &kp);
+    if (st != CP_OK) return st;
+    CP_CUDA(cudaSetDevice(ctx->device));
+    const size_t total = (size_t)n_moves * n_replicas;
+    double *d_init = nullptr;
+    cp_move *d_mv = nullptr;
+    cp_decision *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_init, sizeof(double) * CP_MAX_DOF * n_replicas);
+    if (e == cudaSuccess) e = cudaMalloc(&d_mv, sizeof(cp_move) * total);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(cp_decision) * total);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_init, init_dof, sizeof(double) * CP_MAX_DOF * n_replicas, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mv, moves, sizeof(cp_move) * total, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = CP_DISPATCH(launch_replay, kp.kind, effective_lanes(ctx, kp), kp, d_init, d_mv, n_moves, n_replicas, d_out, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(cp_decision) * total, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_init);
+    cudaFree(d_mv);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "cp_replay");
+    return CP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+"""GPU parity tests (B200): every call goes through the C ABI of lib/libcpgpu.so and is compared
+with the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): overlap predicate, symmetry images and accept/reject decisions
+bit-exact; packing fraction and LJ energy within 1e-6 relative (asserted much tighter where the
+arithmetic is identical); best-packing distributions statistically equivalent for the Philox stream.
+"""
+import ctypes as C
+import json
+import math
+import os
+
+import pytest
+
+import crystal_packing_b200 as cp
+import orc
+from common import GROUPS, c_build, make_states, oracle_scores, random_dofs, same_float
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LJ_RTOL = 1e-6  # north_star tolerance for energies; summation order differs from the reference's
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = cp.Engine(0)
+    yield e
+    e.close()
+
+
+HARD_SPECS = [("polygon", 3), ("polygon", 4), ("polygon", 5), ("polygon", 8), ("polygon", 12),
+              ("radial", (1.0, 0.6, 1.0, 0.6, 1.0, 0.6)), ("trimer",), ("circle",)]
+
+
+# ------------------------------------------------------------------ State::score (overlap predicate)
+@pytest.mark.parametrize("group", GROUPS)
+@pytest.mark.parametrize("spec", HARD_SPECS)
+def test_score_bit_exact_hard(eng, spec, group):
+    cstate, ostate = make_states(spec, group)
+    dofs = [orc.get_dof(ostate)] + random_dofs(ostate, 400, seed=hash((str(spec), group)) & 0xFFFF)
+    ref = oracle_scores(ostate, dofs)
+    assert any(math.isnan(r) for r in ref) and any(not math.isnan(r) for r in ref)
+    for lanes in (0, 4, 8, 16, 32):
+        eng.set_lanes(lanes)
+        got = eng.score(cstate._problem, dofs)
+        bad = [i for i, (a, b) in enumerate(zip(got, ref)) if not same_float(a, b)]
+        assert not bad, (lanes, bad[:5], [(got[i], ref[i], dofs[i]) for i in bad[:2]])
+    eng.set_lanes(0)
+
+
+@pytest.mark.parametrize("group", GROUPS)
+@pytest.mark.parametrize("spec", [("lj_trimer",), ("lj_trimer", 0.63), ("lj_circle",)])
+def test_score_lj_within_tolerance(eng, spec, group):
+    cstate, ostate = make_states(spec, group)
+    dofs = [orc.get_dof(ostate)] + random_dofs(ostate, 200, seed=17)
+    ref = oracle_scores(ostate, dofs)
+    for lanes in (0, 8, 32):
+        eng.set_lanes(lanes)
+        got = eng.score(cstate._problem, dofs)
+        for a, b in zip(got, ref):
+            assert a == pytest.approx(b, rel=LJ_RTOL, abs=1e-12)
+    eng.set_lanes(0)
+
+
+def test_reference_known_answers_on_gpu(eng):
+    # packed.rs:263-267 (square p1 = 1/8), :275-279 analogue through from_group (p2mg = 1/32)
+    sq = cp.LineShape.from_radial("Square", [1.0] * 4)
+    assert cp.PackedState.from_group(sq, "p1").score(eng) == pytest.approx(1 / 8, abs=2.3e-16)
+    assert cp.PackedState.from_group(sq, "p2mg").score(eng) == pytest.approx(1 / 32, abs=2.3e-16)
+    assert cp.PackedState.from_group(sq, "p1").total_shapes() == 1
+    # cell.rs:295-332: unit cell, square of radius 1 / 0.5 overlaps its images, 0.49 does not
+    for r, overlaps in ((1.0, True), (0.5, True), (0.49, False)):
+        s = cp.PackedState.from_group(cp.LineShape.from_radial("Square", [r] * 4), "p1")
+        s.dof = [1.0, 1.0, math.pi / 2, 0.0, 0.0, 0.0]
+        assert (s.score(eng) is None) is overlaps
+    # cell.rs:375-392: skewed cell (1.59, 0.83, 1.21) overlaps
+    s = cp.PackedState.from_group(sq, "p1")
+    s.dof = [1.59, 0.83, 1.21, 0.0, 0.0, 0.0]
+    assert s.score(eng) is None
+    # molecular_shape2.rs:241-274: touching discs do not intersect (strict <)
+    c = cp.PackedState.from_group(cp.MolecularShape2.circle(), "p1")
+    c.dof = [2.0, 1.0, math.pi / 2, 0.0, 0.0, 0.0]
+    assert c.score(eng) == pytest.approx(math.pi / 4, rel=1e-15)
+    c.dof = [1.99, 1.0, math.pi / 2, 0.0, 0.0, 0.0]
+    assert c.score(eng) is None
+    # survey anchor: LJ circle in p1 initial score
+    lj = cp.PotentialState.from_group(cp.LJShape2.circle(), "p1")
+    assert lj.score(eng) == pytest.approx(2.352422182328277, rel=1e-12)
+
+
+# ------------------------------------------------------------------ replayed move sequences
+def dump_moves(spec, group, math_mode, seed, steps=600, inner=200, kt_start=0.1, kt_ratio=0.5):
+    cstate, ostate = make_states(spec, group, math_mode)
+    init = orc.get_dof(ostate)
+    rc, recs, _ = orc.optimise(ostate, kt_start, kt_ratio, 0.01, steps, inner, seed, record=True)
+    assert rc == 0
+    return cstate, init, recs
+
+
+@pytest.mark.parametrize("math_mode", [orc.MATH_CP, orc.MATH_LIBM])
+@pytest.mark.parametrize("spec,group", [(("polygon", 4), "p2"), (("polygon", 5), "p1"),
+                                        (("polygon", 5), "p2"), (("polygon", 5), "p2mg"),
+                                        (("polygon", 5), "p2gg"), (("polygon", 7), "p1g1"),
+                                        (("trimer",), "p2gg"), (("circle",), "p2mm")])
+def test_replay_decisions_bit_exact(eng, spec, group, math_mode):
+    """Accept/reject decisions and Option<score> replayed from oracle-dumped move sequences.  With
+    the oracle on glibc's sin/cos/exp (what the Rust reference executes) the decisions must still
+    match; scores may then differ in the last place (different libm), hence rel 1e-14 there."""
+    seqs, inits, dumps = [], [], []
+    for seed in range(4):
+        cstate, init, recs = dump_moves(spec, group, math_mode, seed)
+        seqs.append([(r.basis_index, r.new_value, 0.0 if math.isnan(r.threshold) else r.threshold, r.kt)
+                     for r in recs])
+        inits.append(init)
+        dumps.append(recs)
+    out = eng.replay(cstate._problem, inits, seqs)
+    for recs, decs in zip(dumps, out):
+        for r, d in zip(recs, decs):
+            assert (d.in_bounds, d.accepted) == (r.in_bounds, r.accepted)
+            assert math.isnan(d.new_score) == math.isnan(r.new_score)  # the overlap predicate
+            if math_mode == orc.MATH_CP:
+                assert same_float(d.new_score, r.new_score) and d.score_current == r.score_current
+            else:
+                assert d.score_current == pytest.approx(r.score_current, rel=1e-14)
+
+
+def test_replay_lj_decisions(eng):
+    seqs, inits, dumps = [], [], []
+    for seed in range(3):
+        cstate, init, recs = dump_moves(("lj_trimer", 0.63), "p2", orc.MATH_CP, seed, steps=300, inner=100)
+        seqs.append([(r.basis_index, r.new_value, 0.0 if math.isnan(r.threshold) else r.threshold, r.kt)
+                     for r in recs])
+        inits.append(init)
+        dumps.append(recs)
+    out = eng.replay(cstate._problem, inits, seqs)
+    n = same = 0
+    for recs, decs in zip(dumps, out):
+        for r, d in zip(recs, decs):
+            n += 1
+            same += (d.in_bounds, d.accepted) == (r.in_bounds, r.accepted)
+            if (d.in_bounds, d.accepted) != (r.in_bounds, r.accepted):
+                break  # after a knife-edge flip the states differ; stop comparing this replica
+            if r.in_bounds:
+                assert d.new_score == pytest.approx(r.new_score, rel=LJ_RTOL)
+    assert same >= n - 3
+
+
+# ------------------------------------------------------------------ free-running trajectories (PCG)
+def run_both(eng, spec, group, bopt, n, begin=0, math_mode=orc.MATH_CP, lanes=0):
+    cstate, ostate = make_states(spec, group, math_mode)
+    eng.set_lanes(lanes)
+    best, res = cp.monte_carlo_best_packing(cstate, c_build(bopt), n, engine=eng,
+                                            replica_begin=begin, return_all=True)
+    eng.set_lanes(0)
+    idx, obest, ores, _ = orc.analyse_state(ostate, bopt, begin, n, n_threads=os.cpu_count() or 1)
+    return best, res, idx, obest, ores
+
+
+TRAJ_CASES = [
+    # BASELINE.json configs[0]: square in p2
+    (("polygon", 4), "p2", dict(steps=2000, inner_steps=500)),
+    # configs[1]: pentagon across p1/p2/p2mg/p2gg
+    (("polygon", 5), "p1", dict(steps=2000, inner_steps=500)),
+    (("polygon", 5), "p2", dict(steps=2000, inner_steps=500)),
+    (("polygon", 5), "p2mg", dict(steps=1500, inner_steps=500)),
+    (("polygon", 5), "p2gg", dict(steps=1500, inner_steps=500)),
+    # configs[2]: trimer in p2gg with the annealing schedule kt 0.1 -> 0.001
+    (("trimer",), "p2gg", dict(steps=1500, inner_steps=500, kt_start=0.1, kt_finish=0.001)),
+    # configs[4] corners: 3- and 12-gons, remaining groups
+    (("polygon", 3), "p1m1", dict(steps=1000, inner_steps=250)),
+    (("polygon", 12), "p2gg", dict(steps=600, inner_steps=200)),
+    (("polygon", 6), "p2mm", dict(steps=1000, inner_steps=250)),
+    (("polygon", 9), "p1g1", dict(steps=1000, inner_steps=250)),
+    (("circle",), "p2", dict(steps=1000, inner_steps=250, kt_ratio=0.2)),
+    # quirks: steps < inner_steps clamps; NaN temperature in stage 3
+    (("polygon", 5), "p2", dict(steps=100, inner_steps=1000)),
+    (("polygon", 4), "p2", dict(steps=900, inner_steps=300, kt_start=0.1, kt_finish=0.01)),
+    # convergence early exit (optimisation.rs:142-159)
+    (("polygon", 5), "p2", dict(steps=6000, inner_steps=200, convergence=1e-3)),
+    # steps not a multiple of inner_steps: the remainder is dropped (optimisation.rs:98)
+    (("polygon", 4), "p1", dict(steps=1150, inner_steps=300)),
+]
+
+
+@pytest.mark.parametrize("spec,group,kw", TRAJ_CASES)
+def test_trajectories_bit_exact(eng, spec, group, kw):
+    """Whole three-stage pipeline per replica with the reference's PCG stream: final DOFs, score,
+    rejection and move counts identical to the oracle for every replica, and the same argmax."""
+    bopt = orc.build_optimiser(**kw)
+    best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 24)
+    for k in range(24):
+        assert list(res[k].dof) == list(ores[k].dof), k
+        assert same_float(res[k].score, ores[k].score), k
+        assert (res[k].rejections, res[k].moves) == (ores[k].rejections, ores[k].moves), k
+    assert best.best_replica == idx and best.best_score == obest.score
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+def test_lane_width_does_not_change_results(eng, lanes):
+    bopt = orc.build_optimiser(steps=800, inner_steps=200)
+    for spec, group in ((("polygon", 5), "p2gg"), (("trimer",), "p2")):
+        best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 16, lanes=lanes)
+        assert [list(r.dof) for r in res] == [list(r.dof) for r in ores]
+        assert [r.score for r in res] == [r.score for r in ores]
+
+
+def test_trajectories_against_glibc_oracle(eng):
+    """Oracle in libm mode = what the Rust reference executes.  DOF trajectories depend only on the
+    RNG stream and the decisions, so they must be bit-identical; the score differs at most in the
+    last place (sin of the cell angle)."""
+    bopt = orc.build_optimiser(steps=2000, inner_steps=500)
+    for spec, group in ((("polygon", 4), "p2"), (("polygon", 5), "p2"), (("trimer",), "p2gg")):
+        best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 32, math_mode=orc.MATH_LIBM)
+        for k in range(32):
+            assert list(res[k].dof) == list(ores[k].dof), (spec, group, k)
+            assert res[k].score == pytest.approx(ores[k].score, rel=1e-14)
+            assert res[k].rejections == ores[k].rejections
+
+
+def test_lj_trajectories(eng):
+    """BASELINE.json configs[3] (LJ trimer / circle).  The energy sum is reduced in a different
+    order on the GPU, so equality is to tolerance; a knife-edge decision may split a trajectory,
+    which is allowed for a small minority of replicas."""
+    bopt = orc.build_optimiser(steps=600, inner_steps=200)
+    for spec, group in ((("lj_trimer",), "p2"), (("lj_circle",), "p1"), (("lj_trimer", 0.63), "p2gg")):
+        best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 16)
+        close = sum(1 for a, b in zip(res, ores) if a.score == pytest.approx(b.score, rel=LJ_RTOL))
+        assert close >= 14, (spec, group, close)
+        assert best.best_score == pytest.approx(obest.score, rel=1e-3)
+
+
+def test_reference_integration_tests(eng):
+    # crystal-packing/tests/packing.rs:14-52 and tests/potential.rs:14-52 through the mirrored API
+    state = cp.PackedState.from_group(cp.LineShape.from_radial("Square", [1.0] * 4), "p2")
+    init = state.score(eng)
+    final_state = cp.MCOptimiser(0.0, 0.0, 0.001, 1000, 100, 0, None).optimise_state(state, eng)
+    assert init < final_state.score(eng)
+    assert (init, final_state.score(eng), final_state.last_rejections) == (0.0625, 0.6424637854786934, 525)
+    lj = cp.PotentialState.from_group(cp.LJShape2.from_trimer(0.63, 120.0, 1.0), "p2")
+    init = lj.score(eng)
+    final_lj = cp.MCOptimiser(0.0, 0.0, 0.001, 1000, 100, 0, None).optimise_state(lj, eng)
+    assert init < final_lj.score(eng)
+    assert final_lj.score(eng) == pytest.approx(2.0102873836561734, rel=LJ_RTOL)
+
+
+def test_invalid_initial_state_is_an_error(eng):
+    # optimisation.rs:81-84: panic!("Invalid configuration passed to function, exiting.")
+    state = cp.PackedState.from_group(cp.LineShape.polygon(4), "p2")
+    state.dof = [0.5, 1.0, math.pi / 2, -0.25, -0.25, 0.0]
+    with pytest.raises(cp.CrystalPackingError) as e:
+        cp.MCOptimiser(0.0, 0.0, 0.001, 100, 100, 0, None).optimise_state(state, eng)
+    assert e.value.status == cp.capi.CP_ERR_INVALID_STATE
+
+
+def test_zero_steps_returns_initial_state(eng):
+    state = cp.PackedState.from_group(cp.LineShape.polygon(5), "p2")
+    out = cp.MCOptimiser(0.1, 0.5, 0.01, 0, 100, 0, None).optimise_state(state, eng)
+    assert out.dof == state.dof
+
+
+# ------------------------------------------------------------------ golden fixtures
+def test_golden_trajectories(eng):
+    """tests/golden/trajectories.json: final states written by tests/golden/make_golden.py from the
+    oracle in libm mode (the Rust reference cannot run here: 'parity unpinned')."""
+    cases = json.load(open(os.path.join(GOLDEN, "trajectories.json")))["cases"]
+    for case in cases:
+        spec = tuple(tuple(x) if isinstance(x, list) else x for x in case["spec"])
+        cstate, _ = make_states(spec, case["group"])
+        b = cp.BuildOptimiser(**case["optimiser"])
+        _, res = cp.monte_carlo_best_packing(cstate, b, len(case["replicas"]), engine=eng, return_all=True)
+        for got, exp in zip(res, case["replicas"]):
+            if case["kind"] == "lj":
+                assert got.score == pytest.approx(float.fromhex(exp["score"]), rel=LJ_RTOL)
+            else:
+                assert [v.hex() for v in got.dof] == exp["dof"]
+                assert got.score == pytest.approx(float.fromhex(exp["score"]), rel=1e-14)
+                assert got.rejections == exp["rejections"]
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def test_full_size_properties(eng):
+    """BASELINE.json configs[1] size: 65,536 pentagon/p2 replicas (Philox stream)."""
+    n = 65536
+    state = cp.PackedState.from_group(cp.LineShape.polygon(5), "p2")
+    opts = cp.BuildOptimiser.cli_defaults(steps=400, inner_steps=100)
+    best, res = cp.monte_carlo_best_packing(state, opts, n, engine=eng, rng=cp.RNG_PHILOX, return_all=True)
+    scores = [r.score for r in res]
+    assert all(0.0 < s <= 1.0 for s in scores)                    # packing fractions, none invalid
+    assert best.best_score == max(scores) and best.best_replica == scores.index(max(scores))
+    assert all(r.moves == 100 + 400 + 400 for r in res)
+    # idempotence: re-scoring the returned states reproduces the reported score bit for bit
+    sample = list(range(0, n, 37))
+    again = eng.score(state._problem, [list(res[i].dof) for i in sample])
+    assert again == [scores[i] for i in sample]
+    # determinism and shard independence: any sub-range reproduces its slice of the full run
+    _, part = cp.monte_carlo_best_packing(state, opts, 1000, engine=eng, rng=cp.RNG_PHILOX,
+                                          replica_begin=40000, return_all=True)
+    assert [list(r.dof) for r in part] == [list(r.dof) for r in res[40000:41000]]
+    # replicas are distinct streams
+    assert len({r.dof[0] for r in res[:2000]}) > 1900
+
+
+def test_philox_statistically_equivalent(eng):
+    """Free-running production stream vs the oracle's PCG stream: same distribution of final packing
+    fractions over replicas (two-sample KS), and the same best packing to 2%."""
+    from scipy.stats import ks_2samp
+
+    n = 768
+    bopt = orc.build_optimiser(steps=1500, inner_steps=500)
+    cstate, ostate = make_states(("polygon", 5), "p2")
+    _, res = cp.monte_carlo_best_packing(cstate, c_build(bopt), n, engine=eng, rng=cp.RNG_PHILOX, return_all=True)
+    _, obest, ores, _ = orc.analyse_state(ostate, bopt, 0, n, n_threads=os.cpu_count() or 1)
+    a, b = [r.score for r in res], [r.score for r in ores]
+    assert ks_2samp(a, b).pvalue > 1e-3
+    assert max(a) == pytest.approx(max(b), rel=0.02)
+    ra, rb = sum(r.rejections for r in res) / n, sum(r.rejections for r in ores) / n
+    assert ra == pytest.approx(rb, rel=0.02)

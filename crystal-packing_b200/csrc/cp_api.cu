@@ -305,15 +305,26 @@ static int auto_lanes(const KProblem &k) {
     return 8;
 }
 
+// dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
+template <typename Kernel>
+static cudaError_t allow_shared(Kernel kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 template <int KIND, int L>
 static cudaError_t launch_mc(const KParams &K, cudaStream_t st) {
     const SharedLayout lay = shared_layout(KIND, K.prob.n_items, K.prob.n_syms, L);
     const unsigned long long gpb = kBlock / L;
     const unsigned grid = (unsigned)((K.n_replicas + gpb - 1) / gpb);
-    if (K.rng_mode == CP_RNG_PCG64MCG)
+    cudaError_t e;
+    if (K.rng_mode == CP_RNG_PCG64MCG) {
+        if ((e = allow_shared(mc_kernel<KIND, L, CP_RNG_PCG64MCG>, lay.bytes)) != cudaSuccess) return e;
         mc_kernel<KIND, L, CP_RNG_PCG64MCG><<<grid, kBlock, lay.bytes, st>>>(K);
-    else
+    } else {
+        if ((e = allow_shared(mc_kernel<KIND, L, CP_RNG_PHILOX>, lay.bytes)) != cudaSuccess) return e;
         mc_kernel<KIND, L, CP_RNG_PHILOX><<<grid, kBlock, lay.bytes, st>>>(K);
+    }
     return cudaGetLastError();
 }
 
@@ -341,6 +352,8 @@ static cudaError_t launch_score(const KProblem &P, const double *dof, unsigned l
                                 cudaStream_t st) {
     const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
     const unsigned long long gpb = kBlock / L;
+    cudaError_t e = allow_shared(score_kernel<KIND, L>, lay.bytes);
+    if (e != cudaSuccess) return e;
     score_kernel<KIND, L><<<(unsigned)((n + gpb - 1) / gpb), kBlock, lay.bytes, st>>>(P, dof, n, out);
     return cudaGetLastError();
 }
@@ -351,6 +364,8 @@ static cudaError_t launch_replay(const KProblem &P, const double *init, const cp
                                  cudaStream_t st) {
     const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
     const unsigned long long gpb = kBlock / L;
+    cudaError_t e = allow_shared(replay_kernel<KIND, L>, lay.bytes);
+    if (e != cudaSuccess) return e;
     replay_kernel<KIND, L><<<(unsigned)((n + gpb - 1) / gpb), kBlock, lay.bytes, st>>>(P, init, mv, n_moves, n, out);
     return cudaGetLastError();
 }

@@ -441,49 +441,78 @@ __device__ __forceinline__ bool hard_overlap(const KProblem &P, const double *s_
     return false;
 }
 
-// PotentialState::score (state/potential.rs:82-115): -(sum of pair energies)/N over in-cell pairs
-// and three shells of images.  The reference accumulates sequentially; here lanes accumulate
-// partial sums that a butterfly combines, so the result agrees to rounding (1e-6 relative is the
-// contract for energies), and is bit-identical across the lanes of the group.
+// LJShape2::energy (shape/lj_shape.rs:35-39): iproduct!(self.items, other.items) summed in order;
+// `other` is shape j displaced by (X, Y) (the rotated points of j plus the image position, or its
+// in-cell placement when in_cell is set).
+__device__ __forceinline__ double shape_energy(const double *s_items, const double *s_shift, Geo g,
+                                               int n, int i, int j, bool in_cell, double X, double Y) {
+    double e = 0.;
+    for (int k = 0; k < n; ++k) {
+        const double *A = g.comp + (i * n + k) * 4;
+        const double *it = s_items + k * 5;
+        for (int l = 0; l < n; ++l) {
+            const double *B = g.comp + (j * n + l) * 4;
+            double ox = in_cell ? B[2] : B[0] + X, oy = in_cell ? B[3] : B[1] + Y;
+            e += lj_pair(A[2] - ox, A[3] - oy, it[2], it[3], it[4], s_shift[k]);
+        }
+    }
+    return e;
+}
+
+// sum += e over the lanes of the group in lane order.  Adding +-0.0 never changes a sum that is not
+// -0.0 (and this sum starts at +0.0, so it never is), hence zero terms are skipped; the non-zero
+// ones are added one by one in the reference's order, in every lane alike.
+template <int L>
+__device__ __forceinline__ double ordered_add(double sum, double e, unsigned gmask) {
+    unsigned nz = group_ballot<L>(gmask, e != 0.0);
+    while (nz) {
+        int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        sum += __shfl_sync(gmask, e, src, L);
+    }
+    return sum;
+}
+
+// PotentialState::score (state/potential.rs:82-115): -(sum of shape-pair energies)/N over the
+// in-cell pairs i < j and then, for every i, j, the 48 images of three shells in iproduct order.
+// Lanes evaluate one shape pair each (the expensive part); the accumulation keeps the reference's
+// sequential order (ordered_add), so the energy is bit-identical to the CPU restatement.
 template <int L>
 __device__ __forceinline__ double lj_score(const KProblem &P, const double *s_items,
                                            const double *s_shift, Geo g, const Dof &d, double sa,
                                            double ca, unsigned gmask, int lane) {
-    const int N = P.n_syms, n = P.n_items, nn = n * n;
+    const int N = P.n_syms, n = P.n_items;
     double sum = 0.;
     const int n_pairs = N * (N - 1) / 2;
-    for (int t = lane; t < n_pairs * nn; t += L) {
-        int q = t / nn, r = t - q * nn;
-        int k = r / n, l = r - k * n;
-        int i, j;
-        pair_from_index(q, N, i, j);
-        const double *A = g.comp + (i * n + k) * 4, *B = g.comp + (j * n + l) * 4;
-        const double *it = s_items + k * 5;
-        sum += lj_pair(A[2] - B[2], A[3] - B[3], it[2], it[3], it[4], s_shift[k]);
+    for (int base = 0; base < n_pairs; base += L) {
+        int q = base + lane;
+        double e = 0.;
+        if (q < n_pairs) {
+            int i, j;
+            pair_from_index(q, N, i, j);
+            e = shape_energy(s_items, s_shift, g, n, i, j, true, 0., 0.);
+        }
+        sum = ordered_add<L>(sum, e, gmask);
     }
     const double a = d.v[0], b = d.v[0] * d.v[1];
     const int side = 7, n_img = 49;  // always 3 shells (potential.rs:105)
     const int total = N * N * n_img;
-    for (int c = lane; c < total; c += L) {
-        int ij = c / n_img, q = c - ij * n_img;
-        int i = ij / N, j = ij - i * N;
-        int ix = q / side - 3, iy = q - (q / side) * side - 3;
-        if (ix == 0 && iy == 0) continue;
-        double fx = g.img[j * 8 + 4] + (double)ix;
-        double fy = g.img[j * 8 + 5] + (double)iy;
-        double yb = fy * b;
-        double X = fx * a + yb * ca, Y = yb * sa;
-        for (int k = 0; k < n; ++k) {
-            const double *A = g.comp + (i * n + k) * 4;
-            const double *it = s_items + k * 5;
-            for (int l = 0; l < n; ++l) {
-                const double *B = g.comp + (j * n + l) * 4;
-                sum += lj_pair(A[2] - (B[0] + X), A[3] - (B[1] + Y), it[2], it[3], it[4], s_shift[k]);
+    for (int base = 0; base < total; base += L) {
+        int c = base + lane;
+        double e = 0.;
+        if (c < total) {
+            int ij = c / n_img, q = c - ij * n_img;
+            int i = ij / N, j = ij - i * N;
+            int ix = q / side - 3, iy = q - (q / side) * side - 3;
+            if (ix != 0 || iy != 0) {
+                double fx = g.img[j * 8 + 4] + (double)ix;
+                double fy = g.img[j * 8 + 5] + (double)iy;
+                double yb = fy * b;
+                e = shape_energy(s_items, s_shift, g, n, i, j, false, fx * a + yb * ca, yb * sa);
             }
         }
+        sum = ordered_add<L>(sum, e, gmask);
     }
-#pragma unroll
-    for (int m = L / 2; m >= 1; m >>= 1) sum += __shfl_xor_sync(gmask, sum, m, L);
     return -sum / (double)N;
 }
 

@@ -227,6 +227,33 @@ class Engine:
         _check(self._lib.cp_last_timing(self._ctx, C.byref(t)))
         return t
 
+    def device_buffers(self):
+        """(results_ptr, best_ptr): device addresses of the prepared job's outputs."""
+        a, b = C.c_void_p(), C.c_void_p()
+        _check(self._lib.cp_device_buffers(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def measure_peaks(self):
+        """(fp64, fp32) FMA TFLOP/s measured on this GPU."""
+        a, b = C.c_double(), C.c_double()
+        _check(self._lib.cp_measure_peaks(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def run_host_buffers(self, problem, schedules, n_replicas, init_ptr, out_ptr, replica_begin=0,
+                         seed_base=0, rng=RNG_PHILOX):
+        """cp_run on caller-owned host buffers given as raw addresses (pinned memory)."""
+        sched = (capi.Schedule * len(schedules))(*schedules)
+        best = capi.Best()
+        _check(self._lib.cp_run(self._ctx, C.byref(problem), sched, len(schedules), rng, seed_base,
+                                replica_begin, n_replicas,
+                                C.cast(init_ptr, C.POINTER(C.c_double)) if init_ptr else None,
+                                C.byref(best),
+                                C.cast(out_ptr, C.POINTER(capi.ReplicaResult)) if out_ptr else None))
+        return best
+
+    def timing_kernel_ms(self):
+        return self.timing().kernel_ms
+
     def replay(self, problem, init_dofs, moves):
         """moves: per replica a list of (basis_index, new_value, threshold, kt)."""
         n, m = len(init_dofs), len(moves[0])

@@ -117,7 +117,9 @@ SIGNATURES = {
     "cp_launch": (_i, [_ctx]),
     "cp_fetch": (_i, [_ctx, _P(Best), _P(ReplicaResult)]),
     "cp_synchronize": (_i, [_ctx]),
+    "cp_device_buffers": (_i, [_ctx, _P(C.c_void_p), _P(C.c_void_p)]),
     "cp_last_timing": (_i, [_ctx, _P(Timing)]),
+    "cp_measure_peaks": (_i, [_ctx, _P(_d), _P(_d)]),
     "cp_score": (_i, [_ctx, _P(Problem), _P(_d), _u64, _P(_d)]),
     "cp_replay": (_i, [_ctx, _P(Problem), _P(_d), _P(Move), _u64, _u64, _P(Decision)]),
 }

@@ -13,6 +13,7 @@
 
 #include "cp_device.cuh"
 #include "cp_internal.h"
+#include "cp_thread.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
@@ -229,7 +230,8 @@ __device__ __forceinline__ bool better(const BestKey &a, const BestKey &b) {
     return a.score > b.score || (a.score == b.score && a.index < b.index);
 }
 __global__ void __launch_bounds__(256)
-best_kernel(const cp_replica_result *res, const BestKey *partial_in, unsigned long long n, BestKey *out) {
+best_kernel(const cp_replica_result *res, const BestKey *partial_in, unsigned long long n, BestKey *out,
+            cp_best *final_best, unsigned long long replica_begin) {
     __shared__ BestKey sh[256];
     BestKey best{__longlong_as_double(0x7FF8000000000000ll), ~0ull};
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -243,7 +245,39 @@ best_kernel(const cp_replica_result *res, const BestKey *partial_in, unsigned lo
         if (threadIdx.x < s && better(sh[threadIdx.x + s], sh[threadIdx.x])) sh[threadIdx.x] = sh[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+    if (threadIdx.x == 0) {
+        out[blockIdx.x] = sh[0];
+        if (final_best) {  // last pass: materialise the winner as a cp_best in device memory
+            cp_best b;
+            if (sh[0].index != ~0ull) {
+                b.result = res[sh[0].index];
+                b.replica = replica_begin + sh[0].index;
+            } else {
+                for (int i = 0; i < CP_MAX_DOF; ++i) b.result.dof[i] = 0.;
+                b.result.score = __longlong_as_double(0x7FF8000000000000ll);
+                b.result.rejections = b.result.moves = 0;
+                b.replica = ~0ull;
+            }
+            *final_best = b;
+        }
+    }
+}
+
+// FP pipe peaks for the roofline denominator: 8 independent FMA chains per thread, no memory traffic
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        if constexpr (sizeof(T) == 8) {
+            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+            x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+        } else {
+            x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+            x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+        }
+    }
+    T r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == (T)123456789) out[blockIdx.x * blockDim.x + threadIdx.x] = r;  // never true; keeps the chains live
 }
 
 // ------------------------------------------------------------------------------------------ context
@@ -260,6 +294,7 @@ struct cp_ctx {
     cp_replica_result *d_out = nullptr;
     double *d_init = nullptr;
     BestKey *d_partial = nullptr;  // [kPartials + 1]
+    cp_best *d_best = nullptr;
     int *d_error = nullptr;
     size_t cap_out = 0, cap_init = 0;
     cp_timing timing{};
@@ -370,7 +405,69 @@ static cudaError_t launch_replay(const KProblem &P, const double *init, const cp
     return cudaGetLastError();
 }
 
-static int effective_lanes(const cp_ctx *ctx, const KProblem &k) { return ctx->lanes ? ctx->lanes : auto_lanes(k); }
+// ---- one thread per replica (cp_thread.cuh); NI = compile-time component count (0 = runtime)
+static size_t thread_shared_bytes(const KProblem &P) {
+    return sizeof(double) * (size_t)kThreadBlock * thread_geo_doubles(P.kind, P.n_items, P.n_syms);
+}
+static bool thread_kernel_fits(const KProblem &P) {
+    return P.kind != CP_LJ && thread_shared_bytes(P) <= 200 * 1024;
+}
+
+template <int KIND, int NI>
+static cudaError_t launch_mc_thread(const KParams &K, cudaStream_t st) {
+    const size_t bytes = thread_shared_bytes(K.prob);
+    const unsigned grid = (unsigned)((K.n_replicas + kThreadBlock - 1) / kThreadBlock);
+    cudaError_t e;
+    if (K.rng_mode == CP_RNG_PCG64MCG) {
+        if ((e = allow_shared(mc_thread_kernel<KIND, NI, CP_RNG_PCG64MCG>, bytes)) != cudaSuccess) return e;
+        mc_thread_kernel<KIND, NI, CP_RNG_PCG64MCG><<<grid, kThreadBlock, bytes, st>>>(K);
+    } else {
+        if ((e = allow_shared(mc_thread_kernel<KIND, NI, CP_RNG_PHILOX>, bytes)) != cudaSuccess) return e;
+        mc_thread_kernel<KIND, NI, CP_RNG_PHILOX><<<grid, kThreadBlock, bytes, st>>>(K);
+    }
+    return cudaGetLastError();
+}
+template <int KIND, int NI>
+static cudaError_t launch_score_thread(const KProblem &P, const double *dof, unsigned long long n, double *out,
+                                       cudaStream_t st) {
+    const size_t bytes = thread_shared_bytes(P);
+    cudaError_t e = allow_shared(score_thread_kernel<KIND, NI>, bytes);
+    if (e != cudaSuccess) return e;
+    score_thread_kernel<KIND, NI><<<(unsigned)((n + kThreadBlock - 1) / kThreadBlock), kThreadBlock, bytes, st>>>(P, dof, n, out);
+    return cudaGetLastError();
+}
+template <int KIND, int NI>
+static cudaError_t launch_replay_thread(const KProblem &P, const double *init, const cp_move *mv,
+                                        unsigned long long n_moves, unsigned long long n, cp_decision *out,
+                                        cudaStream_t st) {
+    const size_t bytes = thread_shared_bytes(P);
+    cudaError_t e = allow_shared(replay_thread_kernel<KIND, NI>, bytes);
+    if (e != cudaSuccess) return e;
+    replay_thread_kernel<KIND, NI><<<(unsigned)((n + kThreadBlock - 1) / kThreadBlock), kThreadBlock, bytes, st>>>(
+        P, init, mv, n_moves, n, out);
+    return cudaGetLastError();
+}
+
+// specialised component counts: pentagon (the headline workload), square, trimer; others run NI = 0
+#define CP_DISPATCH_THREAD(FN, kind, n_items, ...)                                   \
+    [&]() -> cudaError_t {                                                           \
+        if ((kind) == CP_POLYGON) {                                                  \
+            if ((n_items) == 5) return FN<CP_POLYGON, 5>(__VA_ARGS__);               \
+            if ((n_items) == 4) return FN<CP_POLYGON, 4>(__VA_ARGS__);               \
+            return FN<CP_POLYGON, 0>(__VA_ARGS__);                                   \
+        }                                                                            \
+        if ((kind) == CP_DISCS) {                                                    \
+            if ((n_items) == 3) return FN<CP_DISCS, 3>(__VA_ARGS__);                 \
+            return FN<CP_DISCS, 0>(__VA_ARGS__);                                     \
+        }                                                                            \
+        return cudaErrorInvalidValue;                                                \
+    }()
+
+static int effective_lanes(const cp_ctx *ctx, const KProblem &k) {
+    int lanes = ctx->lanes ? ctx->lanes : auto_lanes(k);
+    if (lanes == 1 && !thread_kernel_fits(k)) lanes = 8;  // LJ / very large shapes: group kernel
+    return lanes;
+}
 
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
@@ -410,6 +507,7 @@ cp_status cp_init(int device, cp_ctx **out) {
     for (auto &ev : ctx->ev) CP_CUDA(cudaEventCreate(&ev));
     CP_CUDA(cudaMalloc(&ctx->d_partial, sizeof(BestKey) * (kPartials + 1)));
     CP_CUDA(cudaMalloc(&ctx->d_error, sizeof(int)));
+    CP_CUDA(cudaMalloc(&ctx->d_best, sizeof(cp_best)));
     *out = ctx;
     return CP_OK;
 }
@@ -422,6 +520,7 @@ void cp_destroy(cp_ctx *ctx) {
     cudaFree(ctx->d_init);
     cudaFree(ctx->d_partial);
     cudaFree(ctx->d_error);
+    cudaFree(ctx->d_best);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -436,8 +535,8 @@ cp_status cp_set_stream(cp_ctx *ctx, void *cuda_stream) {
 
 cp_status cp_set_lanes(cp_ctx *ctx, int lanes) {
     if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_set_lanes: null ctx");
-    if (lanes != 0 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
-        return cp_fail(CP_ERR_INVALID_ARG, "cp_set_lanes: lanes must be 0, 4, 8, 16 or 32");
+    if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return cp_fail(CP_ERR_INVALID_ARG, "cp_set_lanes: lanes must be 0, 1, 4, 8, 16 or 32");
     ctx->lanes = lanes;
     return CP_OK;
 }
@@ -508,11 +607,15 @@ cp_status cp_launch(cp_ctx *ctx) {
     const int lanes = effective_lanes(ctx, K.prob);
     CP_CUDA(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
     CP_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CP_CUDA(CP_DISPATCH(launch_mc, K.prob.kind, lanes, K, ctx->stream));
+    if (lanes == 1)
+        CP_CUDA(CP_DISPATCH_THREAD(launch_mc_thread, K.prob.kind, K.prob.n_items, K, ctx->stream));
+    else
+        CP_CUDA(CP_DISPATCH(launch_mc, K.prob.kind, lanes, K, ctx->stream));
     CP_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-    best_kernel<<<kPartials, 256, 0, ctx->stream>>>(ctx->d_out, nullptr, K.n_replicas, ctx->d_partial);
+    best_kernel<<<kPartials, 256, 0, ctx->stream>>>(ctx->d_out, nullptr, K.n_replicas, ctx->d_partial, nullptr, 0);
     CP_CUDA(cudaGetLastError());
-    best_kernel<<<1, 256, 0, ctx->stream>>>(nullptr, ctx->d_partial, kPartials, ctx->d_partial + kPartials);
+    best_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_out, ctx->d_partial, kPartials, ctx->d_partial + kPartials,
+                                            ctx->d_best, K.replica_begin);
     CP_CUDA(cudaGetLastError());
     CP_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     ctx->timing.launches = 3;
@@ -532,26 +635,17 @@ cp_status cp_fetch(cp_ctx *ctx, cp_best *out_best, cp_replica_result *out_all) {
     if (!ctx->launched) return cp_fail(CP_ERR_NOT_PREPARED, "cp_fetch: nothing was launched");
     CP_CUDA(cudaSetDevice(ctx->device));
     const KParams &K = ctx->params;
-    BestKey key{};
+    cp_best best{};
     int err = 0;
     CP_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     if (out_all)
         CP_CUDA(cudaMemcpyAsync(out_all, ctx->d_out, sizeof(cp_replica_result) * K.n_replicas,
                                 cudaMemcpyDeviceToHost, ctx->stream));
-    CP_CUDA(cudaMemcpyAsync(&key, ctx->d_partial + kPartials, sizeof key, cudaMemcpyDeviceToHost, ctx->stream));
+    CP_CUDA(cudaMemcpyAsync(&best, ctx->d_best, sizeof best, cudaMemcpyDeviceToHost, ctx->stream));
     CP_CUDA(cudaMemcpyAsync(&err, ctx->d_error, sizeof err, cudaMemcpyDeviceToHost, ctx->stream));
     CP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     CP_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (out_best) {
-        std::memset(out_best, 0, sizeof *out_best);
-        out_best->result.score = std::nan("");
-        out_best->replica = ~0ull;
-        if (key.index != ~0ull) {
-            CP_CUDA(cudaMemcpy(&out_best->result, ctx->d_out + key.index, sizeof(cp_replica_result),
-                               cudaMemcpyDeviceToHost));
-            out_best->replica = K.replica_begin + key.index;
-        }
-    }
+    if (out_best) *out_best = best;
     float ms = 0.f;
     ctx->timing.h2d_ms = 0.f;
     if (ctx->timed_h2d && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timing.h2d_ms = ms;
@@ -562,8 +656,22 @@ cp_status cp_fetch(cp_ctx *ctx, cp_best *out_best, cp_replica_result *out_all) {
     return CP_OK;
 }
 
+cp_status cp_device_buffers(cp_ctx *ctx, void **d_results, void **d_best) {
+    if (!ctx) return cp_fail(CP_ERR_INVALID_ARG, "cp_device_buffers: null ctx");
+    if (!ctx->prepared) return cp_fail(CP_ERR_NOT_PREPARED, "cp_device_buffers: call cp_prepare first");
+    if (d_results) *d_results = ctx->d_out;
+    if (d_best) *d_best = ctx->d_best;
+    return CP_OK;
+}
+
 cp_status cp_last_timing(cp_ctx *ctx, cp_timing *out) {
     if (!ctx || !out) return cp_fail(CP_ERR_INVALID_ARG, "cp_last_timing: null argument");
+    if (ctx->launched) {  // valid once the stream has passed the events (after a synchronise)
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->timing.kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) ctx->timing.reduce_ms = ms;
+        (void)cudaGetLastError();
+    }
     *out = ctx->timing;
     return CP_OK;
 }
@@ -577,6 +685,41 @@ cp_status cp_run(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stag
     return st;
 }
 
+cp_status cp_measure_peaks(cp_ctx *ctx, double *fp64_tflops, double *fp32_tflops) {
+    if (!ctx || !fp64_tflops || !fp32_tflops) return cp_fail(CP_ERR_INVALID_ARG, "cp_measure_peaks: null argument");
+    CP_CUDA(cudaSetDevice(ctx->device));
+    void *buf = nullptr;
+    CP_CUDA(cudaMalloc(&buf, 8));
+    const int blocks = ctx->sm_count * 8, iters = 1 << 14;
+    cudaEvent_t a = ctx->ev[0], b = ctx->ev[1];
+    double best64 = 0., best32 = 0.;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {
+        float ms = 0.f;
+        cudaEventRecord(a, ctx->stream);
+        fma_peak_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double *)buf, iters, 0.999999, 1e-9);
+        cudaEventRecord(b, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, a, b);
+        double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best64) best64 = tf;
+        cudaEventRecord(a, ctx->stream);
+        fma_peak_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float *)buf, iters * 4, 0.999999f, 1e-9f);
+        cudaEventRecord(b, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, a, b);
+        tf = 2.0 * 8.0 * iters * 4 * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best32) best32 = tf;
+    }
+    cudaFree(buf);
+    if (e != cudaSuccess) return cuda_fail(e, "cp_measure_peaks");
+    *fp64_tflops = best64;
+    *fp32_tflops = best32;
+    return CP_OK;
+}
+
 cp_status cp_score(cp_ctx *ctx, const cp_problem *problem, const double *dof, uint64_t n, double *out_scores) {
     if (!ctx || !dof || !out_scores) return cp_fail(CP_ERR_INVALID_ARG, "cp_score: null argument");
     if (n == 0) return CP_OK;
@@ -588,7 +731,11 @@ cp_status cp_score(cp_ctx *ctx, const cp_problem *problem, const double *dof, ui
     CP_CUDA(cudaMalloc(&d_dof, sizeof(double) * CP_MAX_DOF * n));
     cudaError_t e = cudaMalloc(&d_out, sizeof(double) * n);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_dof, dof, sizeof(double) * CP_MAX_DOF * n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = CP_DISPATCH(launch_score, kp.kind, effective_lanes(ctx, kp), kp, d_dof, n, d_out, ctx->stream);
+    if (e == cudaSuccess) {
+        const int lanes = effective_lanes(ctx, kp);
+        e = lanes == 1 ? CP_DISPATCH_THREAD(launch_score_thread, kp.kind, kp.n_items, kp, d_dof, n, d_out, ctx->stream)
+                       : CP_DISPATCH(launch_score, kp.kind, lanes, kp, d_dof, n, d_out, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_dof);
@@ -614,8 +761,13 @@ cp_status cp_replay(cp_ctx *ctx, const cp_problem *problem, const double *init_d
     if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(cp_decision) * total);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_init, init_dof, sizeof(double) * CP_MAX_DOF * n_replicas, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_mv, moves, sizeof(cp_move) * total, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-        e = CP_DISPATCH(launch_replay, kp.kind, effective_lanes(ctx, kp), kp, d_init, d_mv, n_moves, n_replicas, d_out, ctx->stream);
+    if (e == cudaSuccess) {
+        const int lanes = effective_lanes(ctx, kp);
+        e = lanes == 1 ? CP_DISPATCH_THREAD(launch_replay_thread, kp.kind, kp.n_items, kp, d_init, d_mv, n_moves,
+                                            n_replicas, d_out, ctx->stream)
+                       : CP_DISPATCH(launch_replay, kp.kind, lanes, kp, d_init, d_mv, n_moves, n_replicas, d_out,
+                                     ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(cp_decision) * total, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_init);

@@ -58,6 +58,7 @@ struct Rng {
     unsigned long long key;
     unsigned long long zone;  // Uniform<usize> rejection zone (rand 0.8.4 uniform.rs)
     unsigned long long range;
+    unsigned long long thr;   // Philox: second output word of the move's block (threshold bits)
 };
 
 __device__ __forceinline__ unsigned long long rotr64(unsigned long long v, unsigned r) {
@@ -148,11 +149,15 @@ __device__ __forceinline__ void rng_draw_move(Rng &r, int &basis_index, double &
         }
         sample = u64_to_step(pcg_next(r));
     } else {
+        // one Philox block per move: word a -> step (its top 52 bits), word b -> threshold (its top
+        // 53 bits), the 12 + 11 bits those conversions drop -> basis index (bias <= 6 * 2^-23)
         unsigned long long a, b;
         philox(r.lo, r.hi, r.key, a, b);
         r.lo += 1;
-        basis_index = (int)__umul64hi(a, r.range);  // rejection zone omitted: bias <= 6 * 2^-64
-        sample = u64_to_step(b);
+        r.thr = b;
+        const unsigned spare = (unsigned)(((a & 0xFFFull) << 11) | (b & 0x7FFull));
+        basis_index = (int)((spare * (unsigned)r.range) >> 23);
+        sample = u64_to_step(a);
     }
 }
 
@@ -162,9 +167,7 @@ __device__ __forceinline__ double rng_draw_threshold(Rng &r) {
     if (RNG == CP_RNG_PCG64MCG) {
         return u64_to_unit(pcg_next(r));
     } else {
-        unsigned long long a, b;
-        philox(r.lo | (1ull << 63), r.hi, r.key, a, b);  // disjoint counter half-space
-        return u64_to_unit(a);
+        return u64_to_unit(r.thr);
     }
 }
 

@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing: replicas are independent, so they shard across ranks with no data-path
+collective (the reference's only cross-replica operation is the final `.max()`,
+crystal-packing-cli/src/main.rs:253).  One process per GPU; the single exchange is an all-gather of
+each rank's best replica (80 bytes per rank) followed by the same argmax on every rank.
+
+Works with backend "nccl" on GPUs and "gloo" on CPU tensors (used by the world_size-2 tests).
+"""
+import struct
+
+BEST_BYTES = 80  # sizeof(cp_best): dof[6] f64, score f64, rejections u64, moves u64, replica u64
+_FMT = "<7d3Q"
+
+
+def shard_range(total, rank, world):
+    """Contiguous global replica-id range [begin, begin+count) of `rank`; seeds are global ids, so
+    results do not depend on the number of ranks."""
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, base + (1 if rank < extra else 0)
+
+
+def weak_range(per_rank, rank):
+    return rank * per_rank, per_rank
+
+
+def pack_best(dof, score, rejections, moves, replica):
+    return struct.pack(_FMT, *dof, score, rejections, moves, replica)
+
+
+def unpack_best(buf):
+    v = struct.unpack(_FMT, bytes(buf))
+    return {"dof": list(v[:6]), "score": v[6], "rejections": v[7], "moves": v[8], "replica": v[9]}
+
+
+def pick_best(records):
+    """argmax by score, NaN (None) never wins, ties -> lowest replica id (rayon's max leaves tie
+    order unspecified; this makes it deterministic and independent of the sharding)."""
+    best = None
+    for r in records:
+        if r["score"] != r["score"]:
+            continue
+        if best is None or r["score"] > best["score"] or (
+                r["score"] == best["score"] and r["replica"] < best["replica"]):
+            best = r
+    return best
+
+
+def all_gather_best(local_best_u8, group=None):
+    """local_best_u8: uint8 tensor of BEST_BYTES (on the GPU for nccl, CPU for gloo).  Returns the
+    gathered uint8 tensor [world * BEST_BYTES] on the same device."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    out = torch.empty(world * BEST_BYTES, dtype=torch.uint8, device=local_best_u8.device)
+    dist.all_gather_into_tensor(out, local_best_u8.contiguous(), group=group)
+    return out
+
+
+def global_best(gathered_u8):
+    raw = gathered_u8.cpu().numpy().tobytes()
+    return pick_best([unpack_best(raw[i:i + BEST_BYTES]) for i in range(0, len(raw), BEST_BYTES)])

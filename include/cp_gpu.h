@@ -147,7 +147,8 @@ const char *cp_last_error(void); /* thread-local message of the last failing cal
 const char *cp_version(void);
 /* launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = ctx's own */
 cp_status cp_set_stream(cp_ctx *ctx, void *cuda_stream);
-/* lanes of a warp that cooperate on one replica: 0 = choose automatically, else 4/8/16/32 */
+/* lanes of a warp that cooperate on one replica: 0 = choose automatically; 1 = one thread per
+ * replica (hard shapes; falls back to 8 when the geometry does not fit); 4/8/16/32 = lane groups */
 cp_status cp_set_lanes(cp_ctx *ctx, int lanes);
 
 /* ---- host-side constructors (no GPU work) ----
@@ -190,7 +191,15 @@ cp_status cp_prepare(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *
 cp_status cp_launch(cp_ctx *ctx);
 cp_status cp_fetch(cp_ctx *ctx, cp_best *out_best, cp_replica_result *out_all);
 cp_status cp_synchronize(cp_ctx *ctx);
+/* device addresses of the prepared job's outputs, valid until the next cp_prepare / cp_destroy:
+ * d_results = n_replicas x cp_replica_result, d_best = one cp_best written by cp_launch.  Lets a
+ * multi-GPU host hand the best state to its collective (NCCL) without a host round trip. */
+cp_status cp_device_buffers(cp_ctx *ctx, void **d_results, void **d_best);
 cp_status cp_last_timing(cp_ctx *ctx, cp_timing *out);
+
+/* Measured FP64 / FP32 FMA throughput of this GPU (2 flops per FMA, register-resident chains):
+ * the roofline denominators bench.py reports against (no reference counterpart). */
+cp_status cp_measure_peaks(cp_ctx *ctx, double *fp64_tflops, double *fp32_tflops);
 
 /* State::score for a batch of states (packed.rs:80-86, potential.rs:82-115): dof = n x 6 host
  * doubles, out_scores = n host doubles (NaN = None). */

@@ -302,6 +302,7 @@ void orc_cell_to_cartesian(const orc_state *s, double x, double y, double *ox, d
      * sin of the cell angle on every call */
     double sn, cs;
     orc_sincos(s->math_mode, s->angle, &sn, &cs);
+    g_cnt.trig -= 2; /* the reference re-evaluates cos/sin per call; §8d counts the cell trig once per score */
     *ox = x * cell_a(s) + y * cell_b(s) * cs;
     *oy = y * cell_b(s) * sn;
 }
@@ -311,7 +312,7 @@ double orc_cell_area(const orc_state *s)
     /* cell.rs:190-192 */
     double sn, cs;
     orc_sincos(s->math_mode, s->angle, &sn, &cs);
-    g_cnt.trig -= 1;
+    g_cnt.trig -= 2;
     return sn * cell_a(s) * cell_b(s);
 }
 
@@ -758,6 +759,7 @@ static double potential_score(const orc_state *s)
 double orc_state_score(const orc_state *s)
 {
     g_cnt.scored += 1;
+    g_cnt.trig += 2; /* cos + sin of the cell angle ("cell trig = 2") */
     if (s->kind == ORC_LJ)
         return potential_score(s);
     /* packed.rs:80-86 */

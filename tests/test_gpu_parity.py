@@ -42,7 +42,7 @@ def test_score_bit_exact_hard(eng, spec, group):
     dofs = [orc.get_dof(ostate)] + random_dofs(ostate, 400, seed=hash((str(spec), group)) & 0xFFFF)
     ref = oracle_scores(ostate, dofs)
     assert any(math.isnan(r) for r in ref) and any(not math.isnan(r) for r in ref)
-    for lanes in (0, 4, 8, 16, 32):
+    for lanes in (0, 1, 4, 8, 16, 32):
         eng.set_lanes(lanes)
         got = eng.score(cstate._problem, dofs)
         bad = [i for i, (a, b) in enumerate(zip(got, ref)) if not same_float(a, b)]
@@ -56,7 +56,7 @@ def test_score_lj_bit_exact(eng, spec, group):
     cstate, ostate = make_states(spec, group)
     dofs = [orc.get_dof(ostate)] + random_dofs(ostate, 200, seed=17)
     ref = oracle_scores(ostate, dofs)
-    for lanes in (0, 4, 8, 16, 32):
+    for lanes in (0, 1, 4, 8, 16, 32):
         eng.set_lanes(lanes)
         got = eng.score(cstate._problem, dofs)
         for a, b in zip(got, ref):
@@ -192,13 +192,58 @@ def test_trajectories_bit_exact(eng, spec, group, kw):
     assert best.best_replica == idx and best.best_score == obest.score
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [1, 4, 8, 16, 32])
 def test_lane_width_does_not_change_results(eng, lanes):
     bopt = orc.build_optimiser(steps=800, inner_steps=200)
     for spec, group in ((("polygon", 5), "p2gg"), (("trimer",), "p2")):
         best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 16, lanes=lanes)
         assert [list(r.dof) for r in res] == [list(r.dof) for r in ores]
         assert [r.score for r in res] == [r.score for r in ores]
+
+
+@pytest.mark.parametrize("spec,group,kw", TRAJ_CASES)
+def test_trajectories_bit_exact_thread_kernel(eng, spec, group, kw):
+    """The one-thread-per-replica kernels (lanes = 1) against the oracle, same cases."""
+    bopt = orc.build_optimiser(**kw)
+    best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 70, lanes=1)  # 70: a ragged last block
+    for k in range(70):
+        assert list(res[k].dof) == list(ores[k].dof), k
+        assert same_float(res[k].score, ores[k].score), k
+        assert (res[k].rejections, res[k].moves) == (ores[k].rejections, ores[k].moves), k
+    assert best.best_replica == idx and best.best_score == obest.score
+
+
+def test_philox_stream_is_kernel_independent(eng):
+    """Every kernel variant consumes the Philox stream identically."""
+    state = cp.PackedState.from_group(cp.LineShape.polygon(5), "p2")
+    opts = cp.BuildOptimiser.cli_defaults(steps=600, inner_steps=200)
+    runs = []
+    for lanes in (1, 8, 32):
+        eng.set_lanes(lanes)
+        _, res = cp.monte_carlo_best_packing(state, opts, 200, engine=eng, rng=cp.RNG_PHILOX, return_all=True)
+        runs.append([(list(r.dof), r.score, r.rejections) for r in res])
+    eng.set_lanes(0)
+    assert runs[0] == runs[1] == runs[2]
+
+
+def test_replay_thread_kernel(eng):
+    eng.set_lanes(1)
+    try:
+        for spec, group in ((("polygon", 5), "p2"), (("polygon", 7), "p2gg"), (("trimer",), "p2gg")):
+            seqs, inits, dumps = [], [], []
+            for seed in range(3):
+                cstate, init, recs = dump_moves(spec, group, orc.MATH_CP, seed)
+                seqs.append([(r.basis_index, r.new_value, 0.0 if math.isnan(r.threshold) else r.threshold, r.kt)
+                             for r in recs])
+                inits.append(init)
+                dumps.append(recs)
+            out = eng.replay(cstate._problem, inits, seqs)
+            for recs, decs in zip(dumps, out):
+                for r, d in zip(recs, decs):
+                    assert (d.in_bounds, d.accepted) == (r.in_bounds, r.accepted)
+                    assert same_float(d.new_score, r.new_score) and d.score_current == r.score_current
+    finally:
+        eng.set_lanes(0)
 
 
 def test_trajectories_against_glibc_oracle(eng):
@@ -312,6 +357,8 @@ def test_philox_statistically_equivalent(eng):
     _, obest, ores, _ = orc.analyse_state(ostate, bopt, 0, n, n_threads=os.cpu_count() or 1)
     a, b = [r.score for r in res], [r.score for r in ores]
     assert ks_2samp(a, b).pvalue > 1e-3
-    assert max(a) == pytest.approx(max(b), rel=0.02)
+    qa, qb = sorted(a)[int(0.9 * n)], sorted(b)[int(0.9 * n)]  # upper decile: where the best packings live
+    assert qa == pytest.approx(qb, rel=0.02)
+    assert sum(a) / n == pytest.approx(sum(b) / n, rel=0.01)
     ra, rb = sum(r.rejections for r in res) / n, sum(r.rejections for r in ores) / n
     assert ra == pytest.approx(rb, rel=0.02)

@@ -13,7 +13,7 @@
 
 #include "cp_device.cuh"
 #include "cp_internal.h"
-#include "cp_thread.cuh"
+#include "cp_launch.h"
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
@@ -34,189 +34,6 @@ static cp_status cuda_fail(cudaError_t e, const char *what) {
         cudaError_t e_ = (call);                              \
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
     } while (0)
-
-// ------------------------------------------------------------------------------------------ kernels
-constexpr int kBlock = 128;
-
-struct SharedLayout {
-    int items_off, shift_off, group_off, group_stride, img_doubles;
-    size_t bytes;
-};
-
-__host__ __device__ inline SharedLayout shared_layout(int kind, int n_items, int n_syms, int lanes) {
-    SharedLayout s;
-    const int cw = kind == CP_POLYGON ? 8 : 4;
-    s.items_off = 0;
-    s.shift_off = n_items * 5;
-    s.group_off = s.shift_off + n_items;
-    s.img_doubles = n_syms * 8;
-    s.group_stride = s.img_doubles + n_syms * n_items * cw;
-    s.bytes = sizeof(double) * (size_t)(s.group_off + (kBlock / lanes) * s.group_stride);
-    return s;
-}
-
-template <int KIND, int L>
-__device__ __forceinline__ Geo stage_shared(const KProblem &P, double *smem, const double *&s_items,
-                                            const double *&s_shift) {
-    const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
-    for (int i = threadIdx.x; i < P.n_items * 5; i += kBlock) smem[lay.items_off + i] = P.items[i / 5][i % 5];
-    for (int i = threadIdx.x; i < P.n_items; i += kBlock) smem[lay.shift_off + i] = P.lj_shift[i];
-    __syncthreads();
-    s_items = smem + lay.items_off;
-    s_shift = smem + lay.shift_off;
-    Geo g;
-    g.img = smem + lay.group_off + (threadIdx.x / L) * lay.group_stride;
-    g.comp = g.img + lay.img_doubles;
-    return g;
-}
-
-// The Monte-Carlo optimisation of one replica per group: every stage of MCOptimiser::optimise_state
-// (optimisation.rs:80-180) chained as analyse_state does (main.rs:224-252), annealing schedule,
-// step-size adaptation and convergence counter on the device.
-template <int KIND, int L, int RNG>
-__global__ void __launch_bounds__(kBlock) mc_kernel(const __grid_constant__ KParams K) {
-    extern __shared__ double smem[];
-    const KProblem &P = K.prob;
-    const double *s_items, *s_shift;
-    Geo g = stage_shared<KIND, L>(P, smem, s_items, s_shift);
-    const int lane = threadIdx.x % L;
-    const unsigned gmask = group_mask<L>();
-    const unsigned long long rep = (unsigned long long)blockIdx.x * (kBlock / L) + threadIdx.x / L;
-    if (rep >= K.n_replicas) return;
-    const unsigned long long replica = K.replica_begin + rep;
-
-    Dof d;
-#pragma unroll
-    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = K.init_dof ? K.init_dof[rep * CP_MAX_DOF + i] : P.dof[i];
-
-    const int n_cell = n_cell_dof(P.family);
-    const int n_basis = n_cell + 3;
-    unsigned long long rejections = 0, moves = 0;
-    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
-    bool valid = score_current == score_current;
-    if (!valid && lane == 0) atomicExch(K.error_flag, 1);  // panic!("Invalid configuration ...")
-
-    Rng rng;
-    for (int stage = 0; valid && stage < K.n_stages; ++stage) {
-        const KStage S = K.stages[stage];
-        // generate_basis(): the upper bounds of length and ratio are their values now (cell.rs:139-152)
-        const double len0 = d.v[0], ratio0 = d.v[1];
-        rng_begin_stage<RNG>(rng, K.seed_base + replica, replica, n_basis);
-        double kt = S.kt_start, step_ratio = 1.0;
-        int convergence_count = 0;
-        const unsigned long long outer = S.inner ? S.steps / S.inner : 0ull;
-        bool converged = false;
-        for (unsigned long long loop = 1; loop <= outer && !converged; ++loop) {
-            const double score_start = score_current;
-            unsigned long long loop_rejections = 0;
-            for (unsigned long long it = 0; it < S.inner; ++it) {
-                int basis_index;
-                double sample;
-                rng_draw_move<RNG>(rng, basis_index, sample);
-                const int slot = basis_to_slot(basis_index, n_cell);
-                const double val = d.get(slot);
-                const double new_val = val + S.max_step * step_ratio * sample;  // optimisation.rs:115-119
-                double lo, hi;
-                slot_bounds(slot, len0, ratio0, lo, hi);
-                if (!(lo <= new_val && new_val <= hi)) {  // Basis::set_value Err (basis/mod.rs:31-35)
-                    ++loop_rejections;
-                    continue;
-                }
-                d.set(slot, new_val);
-                const double new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
-                const double threshold = rng_draw_threshold<RNG>(rng);
-                if (accept_move(new_score, score_current, kt, threshold)) {
-                    score_current = new_score;
-                } else {
-                    d.set(slot, val);
-                    ++loop_rejections;
-                }
-            }
-            moves += S.inner;
-            rejections += loop_rejections;
-            kt *= S.kt_ratio;
-            if (S.convergence == S.convergence) {  // Some(precision) (optimisation.rs:142-159)
-                if (score_current - score_start < S.convergence) {
-                    if (++convergence_count > 5) converged = true;
-                } else {
-                    convergence_count = 0;
-                }
-            }
-            if (!converged && step_ratio > 1e-4)  // optimisation.rs:165-167
-                step_ratio *= (double)S.inner / ((double)loop_rejections + 1.);
-        }
-    }
-    if (lane == 0) {
-        cp_replica_result r;
-#pragma unroll
-        for (int i = 0; i < CP_MAX_DOF; ++i) r.dof[i] = d.v[i];
-        r.score = score_current;
-        r.rejections = rejections;
-        r.moves = moves;
-        K.out[rep] = r;
-    }
-}
-
-template <int KIND, int L>
-__global__ void __launch_bounds__(kBlock)
-score_kernel(const __grid_constant__ KProblem P, const double *dof, unsigned long long n, double *out) {
-    extern __shared__ double smem[];
-    const double *s_items, *s_shift;
-    Geo g = stage_shared<KIND, L>(P, smem, s_items, s_shift);
-    const int lane = threadIdx.x % L;
-    const unsigned gmask = group_mask<L>();
-    const unsigned long long rep = (unsigned long long)blockIdx.x * (kBlock / L) + threadIdx.x / L;
-    if (rep >= n) return;
-    Dof d;
-#pragma unroll
-    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = dof[rep * CP_MAX_DOF + i];
-    double s = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
-    if (lane == 0) out[rep] = s;
-}
-
-// the inner-loop body optimisation.rs:104-136 driven by recorded draws
-template <int KIND, int L>
-__global__ void __launch_bounds__(kBlock)
-replay_kernel(const __grid_constant__ KProblem P, const double *init_dof, const cp_move *mv,
-              unsigned long long n_moves, unsigned long long n, cp_decision *out) {
-    extern __shared__ double smem[];
-    const double *s_items, *s_shift;
-    Geo g = stage_shared<KIND, L>(P, smem, s_items, s_shift);
-    const int lane = threadIdx.x % L;
-    const unsigned gmask = group_mask<L>();
-    const unsigned long long rep = (unsigned long long)blockIdx.x * (kBlock / L) + threadIdx.x / L;
-    if (rep >= n) return;
-    Dof d;
-#pragma unroll
-    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = init_dof[rep * CP_MAX_DOF + i];
-    const int n_cell = n_cell_dof(P.family);
-    const double len0 = d.v[0], ratio0 = d.v[1];
-    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
-    for (unsigned long long m = 0; m < n_moves; ++m) {
-        const cp_move M = mv[rep * n_moves + m];
-        const int slot = basis_to_slot((int)M.basis_index, n_cell);
-        const double val = d.get(slot);
-        double lo, hi;
-        slot_bounds(slot, len0, ratio0, lo, hi);
-        cp_decision D;
-        D.in_bounds = 0;
-        D.accepted = 0;
-        D.new_score = __longlong_as_double(0x7FF8000000000000ll);
-        if (lo <= M.new_value && M.new_value <= hi) {
-            D.in_bounds = 1;
-            d.set(slot, M.new_value);
-            D.new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
-            if (accept_move(D.new_score, score_current, M.kt, M.threshold)) {
-                score_current = D.new_score;
-                D.accepted = 1;
-            } else {
-                d.set(slot, val);
-            }
-        }
-        D.score_current = score_current;
-        if (lane == 0) out[rep * n_moves + m] = D;
-    }
-}
 
 // .max() over replicas ordered by score (main.rs:253, packed.rs:49-68); ties keep the lowest index
 struct BestKey {
@@ -340,132 +157,9 @@ static int auto_lanes(const KProblem &k) {
     return 8;
 }
 
-// dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
-template <typename Kernel>
-static cudaError_t allow_shared(Kernel kernel, size_t bytes) {
-    if (bytes <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
-template <int KIND, int L>
-static cudaError_t launch_mc(const KParams &K, cudaStream_t st) {
-    const SharedLayout lay = shared_layout(KIND, K.prob.n_items, K.prob.n_syms, L);
-    const unsigned long long gpb = kBlock / L;
-    const unsigned grid = (unsigned)((K.n_replicas + gpb - 1) / gpb);
-    cudaError_t e;
-    if (K.rng_mode == CP_RNG_PCG64MCG) {
-        if ((e = allow_shared(mc_kernel<KIND, L, CP_RNG_PCG64MCG>, lay.bytes)) != cudaSuccess) return e;
-        mc_kernel<KIND, L, CP_RNG_PCG64MCG><<<grid, kBlock, lay.bytes, st>>>(K);
-    } else {
-        if ((e = allow_shared(mc_kernel<KIND, L, CP_RNG_PHILOX>, lay.bytes)) != cudaSuccess) return e;
-        mc_kernel<KIND, L, CP_RNG_PHILOX><<<grid, kBlock, lay.bytes, st>>>(K);
-    }
-    return cudaGetLastError();
-}
-
-#define CP_DISPATCH(FN, kind, lanes, ...)                                           \
-    [&]() -> cudaError_t {                                                          \
-        switch ((kind) * 100 + (lanes)) {                                           \
-        case CP_POLYGON * 100 + 4: return FN<CP_POLYGON, 4>(__VA_ARGS__);           \
-        case CP_POLYGON * 100 + 8: return FN<CP_POLYGON, 8>(__VA_ARGS__);           \
-        case CP_POLYGON * 100 + 16: return FN<CP_POLYGON, 16>(__VA_ARGS__);         \
-        case CP_POLYGON * 100 + 32: return FN<CP_POLYGON, 32>(__VA_ARGS__);         \
-        case CP_DISCS * 100 + 4: return FN<CP_DISCS, 4>(__VA_ARGS__);               \
-        case CP_DISCS * 100 + 8: return FN<CP_DISCS, 8>(__VA_ARGS__);               \
-        case CP_DISCS * 100 + 16: return FN<CP_DISCS, 16>(__VA_ARGS__);             \
-        case CP_DISCS * 100 + 32: return FN<CP_DISCS, 32>(__VA_ARGS__);             \
-        case CP_LJ * 100 + 4: return FN<CP_LJ, 4>(__VA_ARGS__);                     \
-        case CP_LJ * 100 + 8: return FN<CP_LJ, 8>(__VA_ARGS__);                     \
-        case CP_LJ * 100 + 16: return FN<CP_LJ, 16>(__VA_ARGS__);                   \
-        case CP_LJ * 100 + 32: return FN<CP_LJ, 32>(__VA_ARGS__);                   \
-        default: return cudaErrorInvalidValue;                                      \
-        }                                                                           \
-    }()
-
-template <int KIND, int L>
-static cudaError_t launch_score(const KProblem &P, const double *dof, unsigned long long n, double *out,
-                                cudaStream_t st) {
-    const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
-    const unsigned long long gpb = kBlock / L;
-    cudaError_t e = allow_shared(score_kernel<KIND, L>, lay.bytes);
-    if (e != cudaSuccess) return e;
-    score_kernel<KIND, L><<<(unsigned)((n + gpb - 1) / gpb), kBlock, lay.bytes, st>>>(P, dof, n, out);
-    return cudaGetLastError();
-}
-
-template <int KIND, int L>
-static cudaError_t launch_replay(const KProblem &P, const double *init, const cp_move *mv,
-                                 unsigned long long n_moves, unsigned long long n, cp_decision *out,
-                                 cudaStream_t st) {
-    const SharedLayout lay = shared_layout(KIND, P.n_items, P.n_syms, L);
-    const unsigned long long gpb = kBlock / L;
-    cudaError_t e = allow_shared(replay_kernel<KIND, L>, lay.bytes);
-    if (e != cudaSuccess) return e;
-    replay_kernel<KIND, L><<<(unsigned)((n + gpb - 1) / gpb), kBlock, lay.bytes, st>>>(P, init, mv, n_moves, n, out);
-    return cudaGetLastError();
-}
-
-// ---- one thread per replica (cp_thread.cuh); NI = compile-time component count (0 = runtime)
-static size_t thread_shared_bytes(const KProblem &P) {
-    return sizeof(double) * (size_t)kThreadBlock * thread_geo_doubles(P.kind, P.n_items, P.n_syms);
-}
-static bool thread_kernel_fits(const KProblem &P) {
-    return P.kind != CP_LJ && thread_shared_bytes(P) <= 200 * 1024;
-}
-
-template <int KIND, int NI>
-static cudaError_t launch_mc_thread(const KParams &K, cudaStream_t st) {
-    const size_t bytes = thread_shared_bytes(K.prob);
-    const unsigned grid = (unsigned)((K.n_replicas + kThreadBlock - 1) / kThreadBlock);
-    cudaError_t e;
-    if (K.rng_mode == CP_RNG_PCG64MCG) {
-        if ((e = allow_shared(mc_thread_kernel<KIND, NI, CP_RNG_PCG64MCG>, bytes)) != cudaSuccess) return e;
-        mc_thread_kernel<KIND, NI, CP_RNG_PCG64MCG><<<grid, kThreadBlock, bytes, st>>>(K);
-    } else {
-        if ((e = allow_shared(mc_thread_kernel<KIND, NI, CP_RNG_PHILOX>, bytes)) != cudaSuccess) return e;
-        mc_thread_kernel<KIND, NI, CP_RNG_PHILOX><<<grid, kThreadBlock, bytes, st>>>(K);
-    }
-    return cudaGetLastError();
-}
-template <int KIND, int NI>
-static cudaError_t launch_score_thread(const KProblem &P, const double *dof, unsigned long long n, double *out,
-                                       cudaStream_t st) {
-    const size_t bytes = thread_shared_bytes(P);
-    cudaError_t e = allow_shared(score_thread_kernel<KIND, NI>, bytes);
-    if (e != cudaSuccess) return e;
-    score_thread_kernel<KIND, NI><<<(unsigned)((n + kThreadBlock - 1) / kThreadBlock), kThreadBlock, bytes, st>>>(P, dof, n, out);
-    return cudaGetLastError();
-}
-template <int KIND, int NI>
-static cudaError_t launch_replay_thread(const KProblem &P, const double *init, const cp_move *mv,
-                                        unsigned long long n_moves, unsigned long long n, cp_decision *out,
-                                        cudaStream_t st) {
-    const size_t bytes = thread_shared_bytes(P);
-    cudaError_t e = allow_shared(replay_thread_kernel<KIND, NI>, bytes);
-    if (e != cudaSuccess) return e;
-    replay_thread_kernel<KIND, NI><<<(unsigned)((n + kThreadBlock - 1) / kThreadBlock), kThreadBlock, bytes, st>>>(
-        P, init, mv, n_moves, n, out);
-    return cudaGetLastError();
-}
-
-// specialised component counts: pentagon (the headline workload), square, trimer; others run NI = 0
-#define CP_DISPATCH_THREAD(FN, kind, n_items, ...)                                   \
-    [&]() -> cudaError_t {                                                           \
-        if ((kind) == CP_POLYGON) {                                                  \
-            if ((n_items) == 5) return FN<CP_POLYGON, 5>(__VA_ARGS__);               \
-            if ((n_items) == 4) return FN<CP_POLYGON, 4>(__VA_ARGS__);               \
-            return FN<CP_POLYGON, 0>(__VA_ARGS__);                                   \
-        }                                                                            \
-        if ((kind) == CP_DISCS) {                                                    \
-            if ((n_items) == 3) return FN<CP_DISCS, 3>(__VA_ARGS__);                 \
-            return FN<CP_DISCS, 0>(__VA_ARGS__);                                     \
-        }                                                                            \
-        return cudaErrorInvalidValue;                                                \
-    }()
-
 static int effective_lanes(const cp_ctx *ctx, const KProblem &k) {
     int lanes = ctx->lanes ? ctx->lanes : auto_lanes(k);
-    if (lanes == 1 && !thread_kernel_fits(k)) lanes = 8;  // LJ / very large shapes: group kernel
+    if (lanes == 1 && !cp_thread_kernel_fits(k)) lanes = 8;  // LJ / very large shapes: group kernel
     return lanes;
 }
 
@@ -607,10 +301,7 @@ cp_status cp_launch(cp_ctx *ctx) {
     const int lanes = effective_lanes(ctx, K.prob);
     CP_CUDA(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream));
     CP_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (lanes == 1)
-        CP_CUDA(CP_DISPATCH_THREAD(launch_mc_thread, K.prob.kind, K.prob.n_items, K, ctx->stream));
-    else
-        CP_CUDA(CP_DISPATCH(launch_mc, K.prob.kind, lanes, K, ctx->stream));
+    CP_CUDA(cp_launch_mc(K, lanes, ctx->stream));
     CP_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     best_kernel<<<kPartials, 256, 0, ctx->stream>>>(ctx->d_out, nullptr, K.n_replicas, ctx->d_partial, nullptr, 0);
     CP_CUDA(cudaGetLastError());
@@ -733,8 +424,7 @@ cp_status cp_score(cp_ctx *ctx, const cp_problem *problem, const double *dof, ui
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_dof, dof, sizeof(double) * CP_MAX_DOF * n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         const int lanes = effective_lanes(ctx, kp);
-        e = lanes == 1 ? CP_DISPATCH_THREAD(launch_score_thread, kp.kind, kp.n_items, kp, d_dof, n, d_out, ctx->stream)
-                       : CP_DISPATCH(launch_score, kp.kind, lanes, kp, d_dof, n, d_out, ctx->stream);
+        e = cp_launch_score(kp, lanes, d_dof, n, d_out, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -763,10 +453,7 @@ cp_status cp_replay(cp_ctx *ctx, const cp_problem *problem, const double *init_d
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_mv, moves, sizeof(cp_move) * total, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         const int lanes = effective_lanes(ctx, kp);
-        e = lanes == 1 ? CP_DISPATCH_THREAD(launch_replay_thread, kp.kind, kp.n_items, kp, d_init, d_mv, n_moves,
-                                            n_replicas, d_out, ctx->stream)
-                       : CP_DISPATCH(launch_replay, kp.kind, lanes, kp, d_init, d_mv, n_moves, n_replicas, d_out,
-                                     ctx->stream);
+        e = cp_launch_replay(kp, lanes, d_init, d_mv, n_moves, n_replicas, d_out, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(cp_decision) * total, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -1,0 +1,40 @@
+// cp_launch.h — host-side launch entry points of the kernels, one translation unit per shape kind
+// so that the library builds in parallel (make -j).
+#ifndef CP_LAUNCH_H
+#define CP_LAUNCH_H
+
+#include <cuda_runtime.h>
+
+#include "cp_device.cuh"
+
+// lanes: 1 = one thread per replica (cp_thread.cuh), 4/8/16/32 = lane groups (cp_group.cuh)
+cudaError_t cp_launch_mc(const KParams &K, int lanes, cudaStream_t st);
+cudaError_t cp_launch_score(const KProblem &P, int lanes, const double *dof, unsigned long long n, double *out,
+                            cudaStream_t st);
+cudaError_t cp_launch_replay(const KProblem &P, int lanes, const double *init, const cp_move *mv,
+                             unsigned long long n_moves, unsigned long long n, cp_decision *out, cudaStream_t st);
+// does the per-thread geometry of this problem fit the one-thread-per-replica kernels?
+bool cp_thread_kernel_fits(const KProblem &P);
+
+// per-kind implementations (cp_group_<kind>.cu, cp_thread_<kind>.cu)
+#define CP_DECLARE_KIND(name)                                                                                  \
+    cudaError_t cp_##name##_mc(const KParams &K, int lanes, cudaStream_t st);                                  \
+    cudaError_t cp_##name##_score(const KProblem &P, int lanes, const double *dof, unsigned long long n,       \
+                                  double *out, cudaStream_t st);                                               \
+    cudaError_t cp_##name##_replay(const KProblem &P, int lanes, const double *init, const cp_move *mv,        \
+                                   unsigned long long n_moves, unsigned long long n, cp_decision *out,         \
+                                   cudaStream_t st);
+CP_DECLARE_KIND(group_polygon)
+CP_DECLARE_KIND(group_discs)
+CP_DECLARE_KIND(group_lj)
+CP_DECLARE_KIND(thread_polygon)
+CP_DECLARE_KIND(thread_discs)
+
+// dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
+template <typename Kernel>
+static inline cudaError_t cp_allow_shared(Kernel kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#endif  // CP_LAUNCH_H

@@ -207,6 +207,10 @@ __device__ __forceinline__ void slot_bounds(int slot, double len0, double ratio0
 }
 
 // ------------------------------------------------------------------------------------------ geometry
+struct Trig {
+    double st, ct, sa, ca;  // sin/cos of the site angle (theta) and of the cell angle
+};
+
 // shared-memory view of one group's per-move geometry
 struct Geo {
     double *img;   // [N][8]: m00 m01 m10 m11 | fx fy (fractional, wrapped) | cx cy (Cartesian)
@@ -259,17 +263,18 @@ __device__ __forceinline__ double wrap_unit(double v) {
 //                                                        quotient exceeds 1 + 2^-53 and cannot round to 1)
 // Underflow of t/d needs |t| < 2^-1022 |d|, unreachable for differences of products of O(1)
 // coordinates, and the DOF bounds keep every operand finite.
+// Written without short-circuit operators so that a run of independent tests is one basic block
+// (instruction-level parallelism instead of a branch per test).
 __device__ __forceinline__ bool unit_range(double t, double d) {
-    return t == 0.0 || ((t > 0.0) == (d > 0.0) && fabs(t) <= fabs(d));
+    return (t == 0.0) | (((t > 0.0) == (d > 0.0)) & (fabs(t) <= fabs(d)));
 }
 __device__ __forceinline__ bool segments_cross(double sx, double sy, double sdx, double sdy,
                                                double ox, double oy, double odx, double ody) {
     double u_b = ody * sdx - odx * sdy;
-    if (u_b == 0.0) return false;
     double wy = sy - oy, wx = sx - ox;
     double ua_t = odx * wy - ody * wx;
     double ub_t = sdx * wy - sdy * wx;
-    return unit_range(ua_t, u_b) && unit_range(ub_t, u_b);
+    return (u_b != 0.0) & unit_range(ua_t, u_b) & unit_range(ub_t, u_b);
 }
 
 // LJ2::energy (shape/components/lj2.rs:43-60); parameters of `self` only
@@ -523,10 +528,11 @@ __device__ __forceinline__ double lj_score(const KProblem &P, const double *s_it
 template <int KIND, int L>
 __device__ __forceinline__ double state_score(const KProblem &P, const double *s_items,
                                               const double *s_shift, Geo g, const Dof &d,
-                                              unsigned gmask, int lane) {
-    double st, ct, sa, ca;
-    cp_sincos(d.v[5], &st, &ct);  // Transform2::new(theta, ..) (transform.rs:81-87)
-    cp_sincos(d.v[2], &sa, &ca);  // cell angle (cell.rs:190-192,258-263)
+                                              const Trig &trig, unsigned gmask, int lane) {
+    // trig.st/ct: Transform2::new(theta, ..) (transform.rs:81-87); trig.sa/ca: the cell angle
+    // (cell.rs:190-192,258-263).  The caller keeps them in step with the DOFs: sin/cos are pure
+    // functions of one DOF each, so caching them per DOF is arithmetically identical.
+    const double st = trig.st, ct = trig.ct, sa = trig.sa, ca = trig.ca;
     build_geometry<KIND, L>(P, s_items, g, d, st, ct, sa, ca, gmask, lane);
     double score;
     if (KIND == CP_LJ) {
@@ -539,6 +545,13 @@ __device__ __forceinline__ double state_score(const KProblem &P, const double *s
     }
     __syncwarp(gmask);  // geometry is rewritten by the next move
     return score;
+}
+
+__device__ __forceinline__ Trig trig_of(const Dof &d) {
+    Trig t;
+    cp_sincos(d.v[5], &t.st, &t.ct);
+    cp_sincos(d.v[2], &t.sa, &t.ca);
+    return t;
 }
 
 // MCOptimiser::accept_score (optimisation.rs:55-78) with the threshold already drawn

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kBlock) mc_kernel(const __grid_constant__ KPar
     const int n_cell = n_cell_dof(P.family);
     const int n_basis = n_cell + 3;
     unsigned long long rejections = 0, moves = 0;
-    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+    Trig trig = trig_of(d);
+    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, trig, gmask, lane);
     bool valid = score_current == score_current;
     if (!valid && lane == 0) atomicExch(K.error_flag, 1);  // panic!("Invalid configuration ...")
 
@@ -95,12 +96,21 @@ __global__ void __launch_bounds__(kBlock) mc_kernel(const __grid_constant__ KPar
                     continue;
                 }
                 d.set(slot, new_val);
-                const double new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+                double old_s = 0., old_c = 0.;
+                if (slot == 5 || slot == 2) {  // the only DOFs that enter sin/cos
+                    double s_, c_;
+                    cp_sincos(new_val, &s_, &c_);
+                    if (slot == 5) { old_s = trig.st; old_c = trig.ct; trig.st = s_; trig.ct = c_; }
+                    else { old_s = trig.sa; old_c = trig.ca; trig.sa = s_; trig.ca = c_; }
+                }
+                const double new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, trig, gmask, lane);
                 const double threshold = rng_draw_threshold<RNG>(rng);
                 if (accept_move(new_score, score_current, kt, threshold)) {
                     score_current = new_score;
                 } else {
                     d.set(slot, val);
+                    if (slot == 5) { trig.st = old_s; trig.ct = old_c; }
+                    if (slot == 2) { trig.sa = old_s; trig.ca = old_c; }
                     ++loop_rejections;
                 }
             }
@@ -142,7 +152,7 @@ score_kernel(const __grid_constant__ KProblem P, const double *dof, unsigned lon
     Dof d;
 #pragma unroll
     for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = dof[rep * CP_MAX_DOF + i];
-    double s = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+    double s = state_score<KIND, L>(P, s_items, s_shift, g, d, trig_of(d), gmask, lane);
     if (lane == 0) out[rep] = s;
 }
 
@@ -163,7 +173,7 @@ replay_kernel(const __grid_constant__ KProblem P, const double *init_dof, const 
     for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = init_dof[rep * CP_MAX_DOF + i];
     const int n_cell = n_cell_dof(P.family);
     const double len0 = d.v[0], ratio0 = d.v[1];
-    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+    double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, trig_of(d), gmask, lane);
     for (unsigned long long m = 0; m < n_moves; ++m) {
         const cp_move M = mv[rep * n_moves + m];
         const int slot = basis_to_slot((int)M.basis_index, n_cell);
@@ -177,7 +187,7 @@ replay_kernel(const __grid_constant__ KProblem P, const double *init_dof, const 
         if (lo <= M.new_value && M.new_value <= hi) {
             D.in_bounds = 1;
             d.set(slot, M.new_value);
-            D.new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, gmask, lane);
+            D.new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, trig_of(d), gmask, lane);
             if (accept_move(D.new_score, score_current, M.kt, M.threshold)) {
                 score_current = D.new_score;
                 D.accepted = 1;

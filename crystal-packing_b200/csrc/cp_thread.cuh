@@ -33,10 +33,6 @@ struct TGeo {
     __device__ __forceinline__ void st(int e, double v) const { base[e * kThreadBlock] = v; }
 };
 
-struct Trig {
-    double st, ct, sa, ca;  // sin/cos of the site angle and of the cell angle
-};
-
 template <int KIND, int NI>
 __device__ __forceinline__ void t_build_geometry(const KProblem &P, TGeo g, const Dof &d, const Trig &t) {
     const int N = P.n_syms, n = NI > 0 ? NI : P.n_items;

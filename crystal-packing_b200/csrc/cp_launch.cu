@@ -3,8 +3,7 @@
 #include "cp_thread.cuh"
 
 bool cp_thread_kernel_fits(const KProblem &P) {
-    return P.kind != CP_LJ &&
-           sizeof(double) * (size_t)kThreadBlock * thread_geo_doubles(P.kind, P.n_items, P.n_syms) <= 200 * 1024;
+    return P.kind != CP_LJ && thread_block_shared_bytes(P.kind, P.n_items, P.n_syms) <= 200 * 1024;
 }
 
 cudaError_t cp_launch_mc(const KParams &K, int lanes, cudaStream_t st) {

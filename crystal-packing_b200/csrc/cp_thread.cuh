@@ -117,17 +117,21 @@ __device__ __forceinline__ bool t_shapes_overlap(const KProblem &P, TGeo g, int 
     return hit;
 }
 
-// A queued periodic-image candidate: shape i against image (ix, iy) of shape j, 10 bits
-__device__ __forceinline__ unsigned cand_code(int i, int j, int ix, int iy) {
-    return (unsigned)((i << 8) | (j << 6) | ((ix + 3) << 3) | (iy + 3));
-}
+// A shape-pair candidate of one replica: shape i against image (ix, iy) of shape j, |ix|, |iy| <= 3.
+// Bit q = (ix + 3) * 7 + (iy + 3) of the 64-bit word of the ordered pair (i, j); the centre bit
+// (ix = iy = 0) stands for the in-cell pair i < j, whose displacement to_cartesian(f_j + (0, 0)) is
+// bit for bit j's own Cartesian position (x + 0.0 == x), so one routine tests both kinds.
+constexpr int kCentreBit = 24;
 
-// shape.transform(&transform2) + intersects for one queued candidate of the replica whose geometry
-// is `g` (packed.rs:158-161).  Reads only shared memory, so any lane can evaluate it.
+// shape.transform(&transform2) + intersects for candidate bit q of pair word `ij` of the replica
+// whose geometry is `g` (packed.rs:134-148,158-161).  Reads only shared memory, so any lane of the
+// warp can evaluate it.
 template <int KIND, int NI>
-__device__ __forceinline__ bool t_test_candidate(const KProblem &P, TGeo g, unsigned code) {
-    const int i = (code >> 8) & 3, j = (code >> 6) & 3;
-    const int ix = (int)((code >> 3) & 7) - 3, iy = (int)(code & 7) - 3;
+__device__ __forceinline__ bool t_test_candidate(const KProblem &P, TGeo g, int ij, int q) {
+    const int N = P.n_syms;
+    const int i = ij / N, j = ij - i * N;
+    const int qx = q / 7;
+    const int ix = qx - 3, iy = q - qx * 7 - 3;
     const double a = g.ld(0), b = g.ld(1), ca = g.ld(2), sa = g.ld(3);
     const double fx = g.ld(4 + j * 4 + 0) + (double)ix;  // to_cartesian_translate (cell.rs:241-245)
     const double fy = g.ld(4 + j * 4 + 1) + (double)iy;
@@ -135,23 +139,21 @@ __device__ __forceinline__ bool t_test_candidate(const KProblem &P, TGeo g, unsi
     return t_shapes_overlap<KIND, NI>(P, g, i, j, fx * a + yb * ca, yb * sa);
 }
 
-struct CandQueue {
-    unsigned long long codes = 0;  // up to six 10-bit codes
-    int count = 0;
+// Candidate masks of one thread: N*N words in shared memory, [word][thread]
+struct CandMasks {
+    unsigned long long *base;
+    __device__ __forceinline__ unsigned long long ld(int w) const { return base[w * kThreadBlock]; }
+    __device__ __forceinline__ void st(int w, unsigned long long v) const { base[w * kThreadBlock] = v; }
 };
 
-// PackedState::check_intersection (state/packed.rs:127-167), first part: the in-cell pairs and the
-// distance filter over the periodic images.  Returns true when an overlap is already certain;
-// otherwise the candidates inside 2R are left in `q` for the caller to test (t_drain_local, or the
-// warp-cooperative drain of the MC kernel).
+// PackedState::check_intersection (state/packed.rs:127-167), candidate generation: every in-cell
+// pair i < j (no distance filter there, packed.rs:134-148) and every periodic image that passes
+// the 2R distance filter (packed.rs:150-157) is recorded as a bit; the caller tests them
+// (t_drain_local, or the warp-cooperative drain of the MC kernel).  Returns the number of bits set.
 template <int KIND, int NI>
-__device__ __forceinline__ bool t_sweep(const KProblem &P, TGeo g, const Dof &d, const Trig &t, int shells,
-                                        CandQueue &q) {
+__device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, const Trig &t, int shells,
+                                       CandMasks m) {
     const int N = P.n_syms;
-    for (int i = 0; i < N; ++i)
-        for (int j = i + 1; j < N; ++j)
-            if (t_shapes_overlap<KIND, NI>(P, g, i, j, g.ld(4 + j * 4 + 2), g.ld(4 + j * 4 + 3))) return true;
-
     const double a = d.v[0], b = d.v[0] * d.v[1];
     const double r2x = P.radius * 2.;
     const double radius_sq = r2x * r2x;
@@ -159,11 +161,12 @@ __device__ __forceinline__ bool t_sweep(const KProblem &P, TGeo g, const Dof &d,
     // above radius_sq by a relative 2e-12, far more than the rounding of the reference's
     // dx*dx + dy*dy, so skipping the row leaves every reference decision unchanged.
     const double row_reach = r2x * (1.0 + 1e-12);
-    bool hit = false;
-    for (int i = 0; i < N && !hit; ++i) {
+    int count = 0;
+    for (int i = 0; i < N; ++i) {
         const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
-        for (int j = 0; j < N && !hit; ++j) {
+        for (int j = 0; j < N; ++j) {
             const double fx0 = g.ld(4 + j * 4 + 0), fy0 = g.ld(4 + j * 4 + 1);
+            unsigned long long bits = j > i ? (1ull << kCentreBit) : 0ull;
             for (int iy = -shells; iy <= shells; ++iy) {
                 const double fy = fy0 + (double)iy;  // to_cartesian_translate (cell.rs:241-245)
                 const double yb = fy * b;
@@ -174,80 +177,131 @@ __device__ __forceinline__ bool t_sweep(const KProblem &P, TGeo g, const Dof &d,
                     const double fx = fx0 + (double)ix;
                     const double ddx = cx - (fx * a + ybca);
                     const bool pass = (ddx * ddx + ddy2) <= radius_sq && (ix | iy) != 0;  // packed.rs:156-157
-                    if (pass) {
-                        if (q.count == 6) {  // rare: more than six neighbours in range; test them now
-                            while (q.count > 0 && !hit) {
-                                --q.count;
-                                hit = t_test_candidate<KIND, NI>(P, g, (unsigned)(q.codes & 1023ull));
-                                q.codes >>= 10;
-                            }
-                            q.codes = 0;
-                            q.count = 0;
-                        }
-                        q.codes |= (unsigned long long)cand_code(i, j, ix, iy) << (10 * q.count);
-                        ++q.count;
-                    }
+                    if (pass) bits |= 1ull << ((ix + 3) * 7 + (iy + 3));
                 }
             }
+            m.st(i * N + j, bits);
+            count += __popcll(bits);
         }
     }
-    return hit;
+    return count;
 }
 
-template <int KIND, int NI>
-__device__ __forceinline__ bool t_drain_local(const KProblem &P, TGeo g, CandQueue &q) {
-    bool hit = false;
-    while (q.count > 0 && !hit) {
-        --q.count;
-        hit = t_test_candidate<KIND, NI>(P, g, (unsigned)(q.codes & 1023ull));
-        q.codes >>= 10;
+// pops the next candidate of this thread: in-cell pairs first (they decide most moves), then the
+// image candidates in pair / bit order.  Returns false when none is left.
+__device__ __forceinline__ bool t_pop_candidate(CandMasks m, int NN, int N, int &ij, int &q) {
+    for (int w = 0; w < NN; ++w) {  // in-cell pairs
+        const unsigned long long bits = m.ld(w);
+        if (bits & (1ull << kCentreBit)) {
+            m.st(w, bits & ~(1ull << kCentreBit));
+            ij = w;
+            q = kCentreBit;
+            return true;
+        }
     }
-    return hit;
+    for (int w = 0; w < NN; ++w) {
+        const unsigned long long bits = m.ld(w);
+        if (bits) {
+            q = __ffsll((long long)bits) - 1;
+            m.st(w, bits & (bits - 1));
+            ij = w;
+            return true;
+        }
+    }
+    return false;
 }
 
-// Warp-cooperative drain: the queued candidates of all 32 replicas of the warp are pooled and dealt
-// out evenly, one per lane per round, because their number varies a lot between replicas (0..6+)
-// and a lane-local drain would make every lane wait for the longest queue.  Must be called by all
-// 32 lanes converged.  wq: 192 words + 1 flag word of shared memory per warp.
 template <int KIND, int NI>
-__device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo, unsigned *wq, const CandQueue &q) {
+__device__ __forceinline__ bool t_drain_local(const KProblem &P, TGeo g, CandMasks m) {
+    const int N = P.n_syms, NN = N * N;
+    int ij, q;
+    while (t_pop_candidate(m, NN, N, ij, q))
+        if (t_test_candidate<KIND, NI>(P, g, ij, q)) return true;
+    return false;
+}
+
+// Warp-cooperative drain.  The number of candidates varies a lot between replicas (1 .. dozens in
+// dense, elongated cells), and a lane-local loop would make every lane wait for the longest list
+// while most replicas are decided by their first hit.  So the warp works in rounds: every replica
+// that is still undecided contributes its next few candidates to a pool of at most 32, the lanes
+// test one pool entry each (reading the owner's geometry from shared memory), owners with a hit
+// drop out.  `remaining` = this lane's candidate count (0 for lanes without a proposal).  Must be
+// called by all 32 lanes converged; pool = 33 words of shared memory per warp.
+template <int KIND, int NI>
+__device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo, unsigned long long *smem_masks,
+                                             unsigned *pool, CandMasks m, int remaining) {
     const unsigned lane = threadIdx.x & 31u, warp_first = threadIdx.x & ~31u;
-    int incl = q.count;
+    const int N = P.n_syms, NN = N * N, comp0 = 4 + N * 4;
+    bool hit = false;
+    for (;;) {
+        const unsigned wanting = __ballot_sync(0xffffffffu, remaining > 0);
+        if (wanting == 0u) break;
+        const int quota = 32 / __popc(wanting);  // >= 1; pool never exceeds 32 entries
+        const int take = remaining < quota ? remaining : quota;
+        int incl = take;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int slot = incl - take;
+        for (int k = 0; k < take; ++k) {
+            int ij, q;
+            t_pop_candidate(m, NN, N, ij, q);
+            pool[slot++] = (lane << 10) | (unsigned)(ij << 6) | (unsigned)q;
+        }
+        remaining -= take;
+        if (lane == 0) pool[32] = 0u;
+        __syncwarp();
+        if ((int)lane < total) {
+            const unsigned entry = pool[lane];
+            const unsigned owner = entry >> 10;
+            const TGeo og{smem_geo + warp_first + owner, comp0};
+            if (t_test_candidate<KIND, NI>(P, og, (int)((entry >> 6) & 15u), (int)(entry & 63u)))
+                atomicOr(&pool[32], 1u << owner);
+        }
+        __syncwarp();
+        if ((pool[32] >> lane) & 1u) {
+            hit = true;
+            remaining = 0;  // decided: the rest of this replica's candidates need no test
+        }
+        __syncwarp();  // pool is rewritten by the next round
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return false;
-    const int base = incl - q.count;
-    for (int k = 0; k < q.count; ++k) wq[base + k] = (lane << 10) | (unsigned)((q.codes >> (10 * k)) & 1023ull);
-    if (lane == 0) wq[192] = 0u;
-    __syncwarp();
-    for (int e = (int)lane; e < total; e += 32) {
-        const unsigned entry = wq[e];
-        const unsigned owner = entry >> 10;
-        const TGeo og{smem_geo + warp_first + owner, 0};
-        TGeo gg = og;
-        gg.comp0 = 4 + P.n_syms * 4;
-        if (t_test_candidate<KIND, NI>(P, gg, entry & 1023u)) atomicOr(&wq[192], 1u << owner);
-    }
-    __syncwarp();
-    const bool hit = (wq[192] >> lane) & 1u;
-    __syncwarp();  // wq is rewritten by the next move
     return hit;
 }
 
 // State::score for one replica in one thread, everything local (batch score, replay, initial score)
 template <int KIND, int NI>
-__device__ __forceinline__ double t_state_score(const KProblem &P, TGeo g, const Dof &d, const Trig &t) {
+__device__ __forceinline__ double t_state_score(const KProblem &P, TGeo g, CandMasks m, const Dof &d,
+                                                const Trig &t) {
     t_build_geometry<KIND, NI>(P, g, d, t);
-    CandQueue q;
     const int shells = periodic_range(d.v[0], d.v[0] * d.v[1], d.v[2]);
-    bool overlap = t_sweep<KIND, NI>(P, g, d, t, shells, q);
-    if (!overlap) overlap = t_drain_local<KIND, NI>(P, g, q);
+    t_sweep<KIND, NI>(P, g, d, t, shells, m);
+    const bool overlap = t_drain_local<KIND, NI>(P, g, m);
     const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
     return overlap ? __longlong_as_double(0x7FF8000000000000ll) : (P.area * (double)P.n_syms) / cell_area;
+}
+
+// shared memory of a block: per-thread geometry, per-thread candidate masks, one pool per warp
+__host__ __device__ inline size_t thread_block_shared_bytes(int kind, int n_items, int n_syms) {
+    return sizeof(double) * kThreadBlock * (size_t)(thread_geo_doubles(kind, n_items, n_syms) + n_syms * n_syms) +
+           sizeof(unsigned) * 40 * (kThreadBlock / 32);
+}
+struct ThreadShared {
+    TGeo g;
+    CandMasks m;
+    unsigned long long *masks_all;
+    unsigned *pool;
+};
+__device__ __forceinline__ ThreadShared thread_shared(double *smem, int kind, int n_items, int n_syms) {
+    ThreadShared s;
+    const int geo = thread_geo_doubles(kind, n_items, n_syms);
+    s.g = TGeo{smem + threadIdx.x, 4 + n_syms * 4};
+    s.masks_all = reinterpret_cast<unsigned long long *>(smem + kThreadBlock * geo);
+    s.m = CandMasks{s.masks_all + threadIdx.x};
+    s.pool = reinterpret_cast<unsigned *>(smem + kThreadBlock * (geo + n_syms * n_syms)) + (threadIdx.x >> 5) * 40;
+    return s;
 }
 
 // Monte-Carlo optimisation, one replica per thread (see the header comment for the control flow).
@@ -257,10 +311,8 @@ template <int KIND, int NI, int RNG>
 __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
-    const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
-    // after the per-thread geometry: one candidate pool (192 words + flag) per warp
-    unsigned *wq = reinterpret_cast<unsigned *>(smem + kThreadBlock * thread_geo_doubles(KIND, P.n_items, P.n_syms)) +
-                   (threadIdx.x >> 5) * 200;
+    const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);
+    const TGeo g = sh.g;
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
     const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
     const unsigned long long replica = K.replica_begin + (active ? rep : 0ull);
@@ -276,7 +328,7 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
     const int n_cell = n_cell_dof(P.family);
     const int n_basis = n_cell + 3;
     unsigned long long rejections = 0, moves = 0;
-    double score_current = t_state_score<KIND, NI>(P, g, d, t);
+    double score_current = t_state_score<KIND, NI>(P, g, sh.m, d, t);
     const bool valid = score_current == score_current;
     if (active && !valid) atomicExch(K.error_flag, 1);
     const bool alive = active && valid;
@@ -313,9 +365,8 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
                     if (!have) ++loop_rejections;
                 }
                 if (!__any_sync(0xffffffffu, have)) break;
-                // phase A (lanes holding a proposal): geometry, in-cell pairs, distance filter
-                CandQueue q;
-                bool overlap = false;
+                // phase A (lanes holding a proposal): geometry and candidate generation
+                int candidates = 0;
                 double old_s = 0., old_c = 0.;
                 int old_shells = shells;
                 if (have) {
@@ -328,11 +379,10 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
                     }
                     if (slot <= 2) shells = periodic_range(d.v[0], d.v[0] * d.v[1], d.v[2]);
                     t_build_geometry<KIND, NI>(P, g, d, t);
-                    overlap = t_sweep<KIND, NI>(P, g, d, t, shells, q);
-                    if (overlap) q.count = 0;
+                    candidates = t_sweep<KIND, NI>(P, g, d, t, shells, sh.m);
                 }
-                // phase B (whole warp): the queued image candidates, pooled and shared out
-                overlap |= t_drain_warp<KIND, NI>(P, smem, wq, q);
+                // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
+                const bool overlap = t_drain_warp<KIND, NI>(P, smem, sh.masks_all, sh.pool, sh.m, candidates);
                 // phase C: score and Metropolis decision
                 if (have) {
                     const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
@@ -381,16 +431,13 @@ template <int KIND, int NI>
 __global__ void __launch_bounds__(kThreadBlock)
 score_thread_kernel(const __grid_constant__ KProblem P, const double *dof, unsigned long long n, double *out) {
     extern __shared__ double smem[];
-    const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
+    const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
     if (rep >= n) return;
     Dof d;
 #pragma unroll
     for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = dof[rep * CP_MAX_DOF + i];
-    Trig t;
-    cp_sincos(d.v[5], &t.st, &t.ct);
-    cp_sincos(d.v[2], &t.sa, &t.ca);
-    out[rep] = t_state_score<KIND, NI>(P, g, d, t);
+    out[rep] = t_state_score<KIND, NI>(P, sh.g, sh.m, d, trig_of(d));
 }
 
 template <int KIND, int NI>
@@ -398,7 +445,8 @@ __global__ void __launch_bounds__(kThreadBlock)
 replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof, const cp_move *mv,
                      unsigned long long n_moves, unsigned long long n, cp_decision *out) {
     extern __shared__ double smem[];
-    const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
+    const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);
+    const TGeo g = sh.g;
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
     if (rep >= n) return;
     Dof d;
@@ -409,7 +457,7 @@ replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof,
     const double len0 = d.v[0], ratio0 = d.v[1];
     cp_sincos(d.v[5], &t.st, &t.ct);
     cp_sincos(d.v[2], &t.sa, &t.ca);
-    double score_current = t_state_score<KIND, NI>(P, g, d, t);
+    double score_current = t_state_score<KIND, NI>(P, g, sh.m, d, t);
     for (unsigned long long m = 0; m < n_moves; ++m) {
         const cp_move M = mv[rep * n_moves + m];
         const int slot = basis_to_slot((int)M.basis_index, n_cell);
@@ -425,7 +473,7 @@ replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof,
             d.set(slot, M.new_value);
             cp_sincos(d.v[5], &t.st, &t.ct);
             cp_sincos(d.v[2], &t.sa, &t.ca);
-            D.new_score = t_state_score<KIND, NI>(P, g, d, t);
+            D.new_score = t_state_score<KIND, NI>(P, g, sh.m, d, t);
             if (accept_move(D.new_score, score_current, M.kt, M.threshold)) {
                 score_current = D.new_score;
                 D.accepted = 1;

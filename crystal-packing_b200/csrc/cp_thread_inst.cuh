@@ -4,9 +4,7 @@
 #include "cp_thread.cuh"
 
 static inline size_t thread_shared_bytes(const KProblem &P) {
-    // per-thread geometry + one candidate pool of 200 words per warp (t_drain_warp)
-    return sizeof(double) * (size_t)kThreadBlock * thread_geo_doubles(P.kind, P.n_items, P.n_syms) +
-           sizeof(unsigned) * 200 * (kThreadBlock / 32);
+    return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms);
 }
 
 template <int KIND, int NI>

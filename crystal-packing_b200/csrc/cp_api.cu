@@ -148,7 +148,10 @@ static cp_status make_kproblem(const cp_problem *p, KProblem *k) {
 }
 
 static int auto_lanes(const KProblem &k) {
-    // lanes per replica: enough parallel work per move to keep the lanes busy
+    // Hard shapes: one thread per replica whenever the per-thread geometry fits in shared memory
+    // (measured 4-5x faster than a warp per replica on B200, profiles/README.md).  LJ and very
+    // large shapes: lane groups sized to the parallel work of one move.
+    if (cp_thread_kernel_fits(k)) return 1;
     const int pair_tests = k.n_syms * (k.n_syms - 1) / 2 * k.n_items * k.n_items;
     const int cands = k.n_syms * k.n_syms * (k.kind == CP_LJ ? 48 : 8);
     const int work = pair_tests > cands ? pair_tests : cands;

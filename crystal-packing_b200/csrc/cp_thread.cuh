@@ -127,10 +127,8 @@ constexpr int kCentreBit = 24;
 // whose geometry is `g` (packed.rs:134-148,158-161).  Reads only shared memory, so any lane of the
 // warp can evaluate it.
 template <int KIND, int NI>
-__device__ __forceinline__ bool t_test_candidate(const KProblem &P, TGeo g, int ij, int q) {
-    const int N = P.n_syms;
-    const int i = ij / N, j = ij - i * N;
-    const int qx = q / 7;
+__device__ __forceinline__ bool t_test_candidate(const KProblem &P, TGeo g, int i, int j, int q) {
+    const int qx = (q * 37) >> 8;  // q / 7 for q < 49
     const int ix = qx - 3, iy = q - qx * 7 - 3;
     const double a = g.ld(0), b = g.ld(1), ca = g.ld(2), sa = g.ld(3);
     const double fx = g.ld(4 + j * 4 + 0) + (double)ix;  // to_cartesian_translate (cell.rs:241-245)
@@ -139,41 +137,71 @@ __device__ __forceinline__ bool t_test_candidate(const KProblem &P, TGeo g, int 
     return t_shapes_overlap<KIND, NI>(P, g, i, j, fx * a + yb * ca, yb * sa);
 }
 
-// Candidate masks of one thread: N*N words in shared memory, [word][thread]
+// Candidate masks of one thread: N*N image words in shared memory, [word][thread]; the in-cell
+// pairs (which word's centre bit is meant) and the scan cursor stay in registers.
 struct CandMasks {
     unsigned long long *base;
+    unsigned incell = 0;  // bit w set: in-cell pair of word w still to test
+    int cursor = 0;       // words below it are exhausted
     __device__ __forceinline__ unsigned long long ld(int w) const { return base[w * kThreadBlock]; }
     __device__ __forceinline__ void st(int w, unsigned long long v) const { base[w * kThreadBlock] = v; }
 };
+
+// per-replica values that depend on the cell DOFs only, kept across moves
+struct CellCache {
+    int shells;    // periodic_range (packed.rs:128-132)
+    double inv_a;  // 1 / a, used only to bound the image columns worth testing (never in a decision)
+};
+__device__ __forceinline__ CellCache cell_cache_of(const Dof &d) {
+    CellCache c;
+    c.shells = periodic_range(d.v[0], d.v[0] * d.v[1], d.v[2]);
+    c.inv_a = 1.0 / d.v[0];
+    return c;
+}
 
 // PackedState::check_intersection (state/packed.rs:127-167), candidate generation: every in-cell
 // pair i < j (no distance filter there, packed.rs:134-148) and every periodic image that passes
 // the 2R distance filter (packed.rs:150-157) is recorded as a bit; the caller tests them
 // (t_drain_local, or the warp-cooperative drain of the MC kernel).  Returns the number of bits set.
 template <int KIND, int NI>
-__device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, const Trig &t, int shells,
-                                       CandMasks m) {
-    const int N = P.n_syms;
+__device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, const Trig &t, const CellCache &cc,
+                                       CandMasks &m) {
+    const int N = P.n_syms, shells = cc.shells;
     const double a = d.v[0], b = d.v[0] * d.v[1];
     const double r2x = P.radius * 2.;
     const double radius_sq = r2x * r2x;
-    // A row of images (fixed iy) whose |dy| alone exceeds 2R cannot pass the filter: dy*dy is then
-    // above radius_sq by a relative 2e-12, far more than the rounding of the reference's
-    // dx*dx + dy*dy, so skipping the row leaves every reference decision unchanged.
+    // Exact pruning of the (2*shells+1)^2 image sweep.  A candidate passes only if dx*dx + dy*dy <=
+    // (2R)^2, so (a) a row (fixed iy) with |dy| > 2R(1 + 1e-12) cannot pass, and (b) within a row
+    // only the columns with |dx| <= 2R can: ix in [(u - 2R)/a, (u + 2R)/a] with u the row's offset.
+    // The column bounds are computed approximately and widened by 1e-6 columns (a distance of
+    // 1e-6 * a, against rounding errors of ~1e-15), so every candidate left out fails the
+    // reference's filter by a wide margin; the ones kept are evaluated with the reference's
+    // expressions, bit for bit.
     const double row_reach = r2x * (1.0 + 1e-12);
     int count = 0;
+    m.incell = 0;
+    m.cursor = 0;
     for (int i = 0; i < N; ++i) {
         const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
         for (int j = 0; j < N; ++j) {
             const double fx0 = g.ld(4 + j * 4 + 0), fy0 = g.ld(4 + j * 4 + 1);
-            unsigned long long bits = j > i ? (1ull << kCentreBit) : 0ull;
+            unsigned long long bits = 0ull;
+            if (j > i) {
+                m.incell |= 1u << (i * N + j);
+                ++count;
+            }
             for (int iy = -shells; iy <= shells; ++iy) {
                 const double fy = fy0 + (double)iy;  // to_cartesian_translate (cell.rs:241-245)
                 const double yb = fy * b;
                 const double ddy = cy - yb * t.sa;
                 if (fabs(ddy) > row_reach) continue;
                 const double ybca = yb * t.ca, ddy2 = ddy * ddy;
-                for (int ix = -shells; ix <= shells; ++ix) {
+                const double u = (cx - ybca) * cc.inv_a - fx0;  // column where dx would vanish
+                const double w = r2x * cc.inv_a + 1e-6;
+                int lo = __double2int_ru(u - w), hi = __double2int_rd(u + w);
+                lo = lo < -shells ? -shells : lo;
+                hi = hi > shells ? shells : hi;
+                for (int ix = lo; ix <= hi; ++ix) {
                     const double fx = fx0 + (double)ix;
                     const double ddx = cx - (fx * a + ybca);
                     const bool pass = (ddx * ddx + ddy2) <= radius_sq && (ix | iy) != 0;  // packed.rs:156-157
@@ -189,34 +217,34 @@ __device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, 
 
 // pops the next candidate of this thread: in-cell pairs first (they decide most moves), then the
 // image candidates in pair / bit order.  Returns false when none is left.
-__device__ __forceinline__ bool t_pop_candidate(CandMasks m, int NN, int N, int &ij, int &q) {
-    for (int w = 0; w < NN; ++w) {  // in-cell pairs
-        const unsigned long long bits = m.ld(w);
-        if (bits & (1ull << kCentreBit)) {
-            m.st(w, bits & ~(1ull << kCentreBit));
-            ij = w;
-            q = kCentreBit;
-            return true;
-        }
+__device__ __forceinline__ bool t_pop_candidate(CandMasks &m, int NN, int &ij, int &q) {
+    if (m.incell) {
+        ij = __ffs((int)m.incell) - 1;
+        m.incell &= m.incell - 1;
+        q = kCentreBit;
+        return true;
     }
-    for (int w = 0; w < NN; ++w) {
-        const unsigned long long bits = m.ld(w);
+    while (m.cursor < NN) {
+        const unsigned long long bits = m.ld(m.cursor);
         if (bits) {
             q = __ffsll((long long)bits) - 1;
-            m.st(w, bits & (bits - 1));
-            ij = w;
+            m.st(m.cursor, bits & (bits - 1));
+            ij = m.cursor;
             return true;
         }
+        ++m.cursor;
     }
     return false;
 }
 
 template <int KIND, int NI>
-__device__ __forceinline__ bool t_drain_local(const KProblem &P, TGeo g, CandMasks m) {
+__device__ __forceinline__ bool t_drain_local(const KProblem &P, TGeo g, CandMasks &m) {
     const int N = P.n_syms, NN = N * N;
     int ij, q;
-    while (t_pop_candidate(m, NN, N, ij, q))
-        if (t_test_candidate<KIND, NI>(P, g, ij, q)) return true;
+    while (t_pop_candidate(m, NN, ij, q)) {
+        const int i = ij / N;
+        if (t_test_candidate<KIND, NI>(P, g, i, ij - i * N, q)) return true;
+    }
     return false;
 }
 
@@ -228,8 +256,8 @@ __device__ __forceinline__ bool t_drain_local(const KProblem &P, TGeo g, CandMas
 // drop out.  `remaining` = this lane's candidate count (0 for lanes without a proposal).  Must be
 // called by all 32 lanes converged; pool = 33 words of shared memory per warp.
 template <int KIND, int NI>
-__device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo, unsigned long long *smem_masks,
-                                             unsigned *pool, CandMasks m, int remaining) {
+__device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo, unsigned *pool, CandMasks &m,
+                                             int remaining) {
     const unsigned lane = threadIdx.x & 31u, warp_first = threadIdx.x & ~31u;
     const int N = P.n_syms, NN = N * N, comp0 = 4 + N * 4;
     bool hit = false;
@@ -248,8 +276,9 @@ __device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo
         int slot = incl - take;
         for (int k = 0; k < take; ++k) {
             int ij, q;
-            t_pop_candidate(m, NN, N, ij, q);
-            pool[slot++] = (lane << 10) | (unsigned)(ij << 6) | (unsigned)q;
+            t_pop_candidate(m, NN, ij, q);
+            const int i = N == 1 ? 0 : (N == 2 ? ij >> 1 : (N == 4 ? ij >> 2 : (ij * 11) >> 5));  // ij / N, N <= 4
+            pool[slot++] = (lane << 10) | (unsigned)(i << 8) | (unsigned)((ij - i * N) << 6) | (unsigned)q;
         }
         remaining -= take;
         if (lane == 0) pool[32] = 0u;
@@ -258,7 +287,8 @@ __device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo
             const unsigned entry = pool[lane];
             const unsigned owner = entry >> 10;
             const TGeo og{smem_geo + warp_first + owner, comp0};
-            if (t_test_candidate<KIND, NI>(P, og, (int)((entry >> 6) & 15u), (int)(entry & 63u)))
+            if (t_test_candidate<KIND, NI>(P, og, (int)((entry >> 8) & 3u), (int)((entry >> 6) & 3u),
+                                           (int)(entry & 63u)))
                 atomicOr(&pool[32], 1u << owner);
         }
         __syncwarp();
@@ -276,8 +306,7 @@ template <int KIND, int NI>
 __device__ __forceinline__ double t_state_score(const KProblem &P, TGeo g, CandMasks m, const Dof &d,
                                                 const Trig &t) {
     t_build_geometry<KIND, NI>(P, g, d, t);
-    const int shells = periodic_range(d.v[0], d.v[0] * d.v[1], d.v[2]);
-    t_sweep<KIND, NI>(P, g, d, t, shells, m);
+    t_sweep<KIND, NI>(P, g, d, t, cell_cache_of(d), m);
     const bool overlap = t_drain_local<KIND, NI>(P, g, m);
     const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
     return overlap ? __longlong_as_double(0x7FF8000000000000ll) : (P.area * (double)P.n_syms) / cell_area;
@@ -299,7 +328,7 @@ __device__ __forceinline__ ThreadShared thread_shared(double *smem, int kind, in
     const int geo = thread_geo_doubles(kind, n_items, n_syms);
     s.g = TGeo{smem + threadIdx.x, 4 + n_syms * 4};
     s.masks_all = reinterpret_cast<unsigned long long *>(smem + kThreadBlock * geo);
-    s.m = CandMasks{s.masks_all + threadIdx.x};
+    s.m.base = s.masks_all + threadIdx.x;
     s.pool = reinterpret_cast<unsigned *>(smem + kThreadBlock * (geo + n_syms * n_syms)) + (threadIdx.x >> 5) * 40;
     return s;
 }
@@ -334,7 +363,8 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
     const bool alive = active && valid;
 
     Rng rng;
-    int shells = periodic_range(d.v[0], d.v[0] * d.v[1], d.v[2]);  // depends on the cell DOFs only
+    CellCache cc = cell_cache_of(d);
+    CandMasks masks = sh.m;
     for (int stage = 0; stage < K.n_stages; ++stage) {
         const KStage S = K.stages[stage];
         const double len0 = d.v[0], ratio0 = d.v[1];
@@ -368,7 +398,7 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
                 // phase A (lanes holding a proposal): geometry and candidate generation
                 int candidates = 0;
                 double old_s = 0., old_c = 0.;
-                int old_shells = shells;
+                const CellCache old_cc = cc;
                 if (have) {
                     d.set(slot, new_val);
                     if (slot == 5 || slot == 2) {  // only these two DOFs enter sin/cos
@@ -377,12 +407,12 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
                         if (slot == 5) { old_s = t.st; old_c = t.ct; t.st = s_; t.ct = c_; }
                         else { old_s = t.sa; old_c = t.ca; t.sa = s_; t.ca = c_; }
                     }
-                    if (slot <= 2) shells = periodic_range(d.v[0], d.v[0] * d.v[1], d.v[2]);
+                    if (slot <= 2) cc = cell_cache_of(d);
                     t_build_geometry<KIND, NI>(P, g, d, t);
-                    candidates = t_sweep<KIND, NI>(P, g, d, t, shells, sh.m);
+                    candidates = t_sweep<KIND, NI>(P, g, d, t, cc, masks);
                 }
                 // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
-                const bool overlap = t_drain_warp<KIND, NI>(P, smem, sh.masks_all, sh.pool, sh.m, candidates);
+                const bool overlap = t_drain_warp<KIND, NI>(P, smem, sh.pool, masks, candidates);
                 // phase C: score and Metropolis decision
                 if (have) {
                     const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
@@ -395,7 +425,7 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
                         d.set(slot, val);
                         if (slot == 5) { t.st = old_s; t.ct = old_c; }
                         if (slot == 2) { t.sa = old_s; t.ca = old_c; }
-                        shells = old_shells;
+                        cc = old_cc;
                         ++loop_rejections;
                     }
                 }

@@ -138,6 +138,16 @@ static cp_status make_kproblem(const cp_problem *p, KProblem *k) {
     std::memcpy(k->dof, p->dof, sizeof k->dof);
     k->area = p->area;
     k->radius = p->enclosing_radius;
+    k->lj_reach = INFINITY;
+    if (p->kind == CP_LJ) {
+        double cmax = 0., rmax = 0.;
+        for (int i = 0; i < p->n_items; ++i) {
+            const double x = p->items[i][4];
+            cmax = std::isnan(x) ? INFINITY : std::fmax(cmax, x);
+            rmax = std::fmax(rmax, std::sqrt(p->items[i][0] * p->items[i][0] + p->items[i][1] * p->items[i][1]));
+        }
+        k->lj_reach = cmax + 2. * rmax;
+    }
     if (p->kind == CP_LJ)
         for (int i = 0; i < p->n_items; ++i) {
             const double sigma = p->items[i][2], eps = p->items[i][3], x = p->items[i][4];

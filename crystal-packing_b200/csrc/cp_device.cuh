@@ -30,6 +30,7 @@ struct KProblem {
     double area, radius;
     double dof[CP_MAX_DOF];
     double lj_shift[CP_MAX_ITEMS];  // 4*eps*((sigma/x)^12 - (sigma/x)^6) per site (lj2.rs:50-51)
+    double lj_reach;  // max cutoff + 2 * max |site position|; +inf when a site has no cutoff
 };
 
 struct KStage {
@@ -264,17 +265,15 @@ __device__ __forceinline__ double wrap_unit(double v) {
 // Underflow of t/d needs |t| < 2^-1022 |d|, unreachable for differences of products of O(1)
 // coordinates, and the DOF bounds keep every operand finite.
 // Written without short-circuit operators so that a run of independent tests is one basic block
-// (instruction-level parallelism instead of a branch per test).  The sign and zero tests read the
-// bit patterns in the integer ALU and only the magnitude comparison stays on the FP64 pipe, which
-// is the busiest unit of these kernels:
-//   t == 0 or sign(t) == sign(d)   <=>  t is +-0, or the sign bits of t and d agree
-// (d != 0 is guaranteed by the caller's u_b != 0 factor; operands are finite by the DOF bounds).
-__device__ __forceinline__ bool is_zero(double v) {
-    return ((__double2hiint(v) & 0x7fffffff) | __double2loint(v)) == 0;
-}
+// (instruction-level parallelism instead of a branch per test).  With tt = t carrying d's sign
+// flipped onto it (the bit pattern of t * sign(d), one integer XOR):
+//   t == 0 or sign(t) == sign(d)   <=>  tt >= 0      (-0 >= 0 holds in IEEE comparison)
+//   and then  |t| <= |d|           <=>  tt <= |d|
+// so each quotient test is two chained FP64 compares.  d != 0 is the caller's u_b != 0 factor;
+// operands are finite by the DOF bounds.
 __device__ __forceinline__ bool unit_range(double t, double d) {
-    const bool same_sign = (__double2hiint(t) ^ __double2hiint(d)) >= 0;
-    return (fabs(t) <= fabs(d)) & (same_sign | is_zero(t));
+    const double tt = __hiloint2double(__double2hiint(t) ^ (__double2hiint(d) & (int)0x80000000), __double2loint(t));
+    return (tt >= 0.0) & (tt <= fabs(d));
 }
 __device__ __forceinline__ bool segments_cross(double sx, double sy, double sdx, double sdy,
                                                double ox, double oy, double odx, double ody) {
@@ -282,7 +281,7 @@ __device__ __forceinline__ bool segments_cross(double sx, double sy, double sdx,
     double wy = sy - oy, wx = sx - ox;
     double ua_t = odx * wy - ody * wx;
     double ub_t = sdx * wy - sdy * wx;
-    return (!is_zero(u_b)) & unit_range(ua_t, u_b) & unit_range(ub_t, u_b);
+    return (u_b != 0.0) & unit_range(ua_t, u_b) & unit_range(ub_t, u_b);
 }
 
 // LJ2::energy (shape/components/lj2.rs:43-60); parameters of `self` only

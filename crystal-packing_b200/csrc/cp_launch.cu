@@ -3,14 +3,14 @@
 #include "cp_thread.cuh"
 
 bool cp_thread_kernel_fits(const KProblem &P) {
-    return P.kind != CP_LJ && thread_block_shared_bytes(P.kind, P.n_items, P.n_syms) <= 200 * 1024;
+    return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms) <= 200 * 1024;
 }
 
 cudaError_t cp_launch_mc(const KParams &K, int lanes, cudaStream_t st) {
     switch (K.prob.kind) {
     case CP_POLYGON: return lanes == 1 ? cp_thread_polygon_mc(K, lanes, st) : cp_group_polygon_mc(K, lanes, st);
     case CP_DISCS: return lanes == 1 ? cp_thread_discs_mc(K, lanes, st) : cp_group_discs_mc(K, lanes, st);
-    case CP_LJ: return cp_group_lj_mc(K, lanes, st);
+    case CP_LJ: return lanes == 1 ? cp_thread_lj_mc(K, lanes, st) : cp_group_lj_mc(K, lanes, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -24,7 +24,8 @@ cudaError_t cp_launch_score(const KProblem &P, int lanes, const double *dof, uns
     case CP_DISCS:
         return lanes == 1 ? cp_thread_discs_score(P, lanes, dof, n, out, st)
                           : cp_group_discs_score(P, lanes, dof, n, out, st);
-    case CP_LJ: return cp_group_lj_score(P, lanes, dof, n, out, st);
+    case CP_LJ:
+        return lanes == 1 ? cp_thread_lj_score(P, lanes, dof, n, out, st) : cp_group_lj_score(P, lanes, dof, n, out, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -38,7 +39,9 @@ cudaError_t cp_launch_replay(const KProblem &P, int lanes, const double *init, c
     case CP_DISCS:
         return lanes == 1 ? cp_thread_discs_replay(P, lanes, init, mv, n_moves, n, out, st)
                           : cp_group_discs_replay(P, lanes, init, mv, n_moves, n, out, st);
-    case CP_LJ: return cp_group_lj_replay(P, lanes, init, mv, n_moves, n, out, st);
+    case CP_LJ:
+        return lanes == 1 ? cp_thread_lj_replay(P, lanes, init, mv, n_moves, n, out, st)
+                          : cp_group_lj_replay(P, lanes, init, mv, n_moves, n, out, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -29,6 +29,7 @@ CP_DECLARE_KIND(group_discs)
 CP_DECLARE_KIND(group_lj)
 CP_DECLARE_KIND(thread_polygon)
 CP_DECLARE_KIND(thread_discs)
+CP_DECLARE_KIND(thread_lj)
 
 // dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
 template <typename Kernel>

@@ -301,15 +301,82 @@ __device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo
     return hit;
 }
 
+template <int NI>
+__device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Dof &d, const Trig &t,
+                                             const CellCache &cc);
+
 // State::score for one replica in one thread, everything local (batch score, replay, initial score)
 template <int KIND, int NI>
 __device__ __forceinline__ double t_state_score(const KProblem &P, TGeo g, CandMasks m, const Dof &d,
                                                 const Trig &t) {
+    if constexpr (KIND == CP_LJ) return t_lj_score<NI>(P, g, d, t, cell_cache_of(d));
     t_build_geometry<KIND, NI>(P, g, d, t);
     t_sweep<KIND, NI>(P, g, d, t, cell_cache_of(d), m);
     const bool overlap = t_drain_local<KIND, NI>(P, g, m);
     const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
     return overlap ? __longlong_as_double(0x7FF8000000000000ll) : (P.area * (double)P.n_syms) / cell_area;
+}
+
+// LJShape2::energy (shape/lj_shape.rs:35-39): iproduct!(self.items, other.items) summed in order,
+// `other` = shape j displaced to (X, Y)
+template <int NI>
+__device__ __forceinline__ double t_shape_energy(const KProblem &P, TGeo g, int i, int j, double X, double Y) {
+    const int n = NI > 0 ? NI : P.n_items;
+    const int ei = g.comp0 + i * n * 2, ej = g.comp0 + j * n * 2;
+    const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
+    double e = 0.;
+#pragma unroll
+    for (int k = 0; k < (NI > 0 ? NI : CP_MAX_ITEMS); ++k) {
+        if (NI == 0 && k >= n) break;
+        const double sx = g.ld(ei + k * 2 + 0) + cx, sy = g.ld(ei + k * 2 + 1) + cy;
+        const double *it = P.items[k];
+#pragma unroll
+        for (int l = 0; l < (NI > 0 ? NI : CP_MAX_ITEMS); ++l) {
+            if (NI == 0 && l >= n) break;
+            const double ox = g.ld(ej + l * 2 + 0) + X, oy = g.ld(ej + l * 2 + 1) + Y;
+            e += lj_pair(sx - ox, sy - oy, it[2], it[3], it[4], P.lj_shift[k]);
+        }
+    }
+    return e;
+}
+
+// PotentialState::score (state/potential.rs:82-115) for one replica in one thread: the reference's
+// accumulation order is simply the loop order here.  Exact pruning: when every site has a cutoff,
+// a shape pair whose centres are further apart than max cutoff + 2 max|site| (P.lj_reach, widened
+// by 1e-9) has all its site distances beyond the cutoff, each LJ2::energy is exactly 0.0 and adding
+// it cannot change the sum - so the pair, its row or its columns are skipped outright.
+template <int NI>
+__device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Dof &d, const Trig &t,
+                                             const CellCache &cc) {
+    t_build_geometry<CP_LJ, NI>(P, g, d, t);
+    const int N = P.n_syms;
+    const double a = d.v[0], b = d.v[0] * d.v[1];
+    const double reach = P.lj_reach * (1.0 + 1e-9);  // +inf: no pruning
+    const double reach_sq = reach * reach;
+    double sum = 0.;
+    for (int i = 0; i < N; ++i)
+        for (int j = i + 1; j < N; ++j)
+            sum += t_shape_energy<NI>(P, g, i, j, g.ld(4 + j * 4 + 2), g.ld(4 + j * 4 + 3));
+    for (int i = 0; i < N; ++i) {
+        const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
+        for (int j = 0; j < N; ++j) {
+            const double fx0 = g.ld(4 + j * 4 + 0), fy0 = g.ld(4 + j * 4 + 1);
+            for (int ix = -3; ix <= 3; ++ix) {  // periodic_images(position, 3, false): x outer, y inner
+                const double fx = fx0 + (double)ix;
+                const double xa = fx * a;
+                for (int iy = -3; iy <= 3; ++iy) {
+                    if ((ix | iy) == 0) continue;
+                    const double fy = fy0 + (double)iy;
+                    const double yb = fy * b;
+                    const double X = xa + yb * t.ca, Y = yb * t.sa;
+                    const double ddx = cx - X, ddy = cy - Y;
+                    if (ddx * ddx + ddy * ddy > reach_sq) continue;  // every site pair beyond its cutoff
+                    sum += t_shape_energy<NI>(P, g, i, j, X, Y);
+                }
+            }
+        }
+    }
+    return -sum / (double)N;
 }
 
 // shared memory of a block: per-thread geometry, per-thread candidate masks, one pool per warp
@@ -397,7 +464,7 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
                 if (!__any_sync(0xffffffffu, have)) break;
                 // phase A (lanes holding a proposal): geometry and candidate generation
                 int candidates = 0;
-                double old_s = 0., old_c = 0.;
+                double old_s = 0., old_c = 0., lj_score = 0.;
                 const CellCache old_cc = cc;
                 if (have) {
                     d.set(slot, new_val);
@@ -408,16 +475,26 @@ __global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid
                         else { old_s = t.sa; old_c = t.ca; t.sa = s_; t.ca = c_; }
                     }
                     if (slot <= 2) cc = cell_cache_of(d);
-                    t_build_geometry<KIND, NI>(P, g, d, t);
-                    candidates = t_sweep<KIND, NI>(P, g, d, t, cc, masks);
+                    if constexpr (KIND == CP_LJ) {
+                        lj_score = t_lj_score<NI>(P, g, d, t, cc);
+                    } else {
+                        t_build_geometry<KIND, NI>(P, g, d, t);
+                        candidates = t_sweep<KIND, NI>(P, g, d, t, cc, masks);
+                    }
                 }
                 // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
-                const bool overlap = t_drain_warp<KIND, NI>(P, smem, sh.pool, masks, candidates);
+                bool overlap = false;
+                if constexpr (KIND != CP_LJ) overlap = t_drain_warp<KIND, NI>(P, smem, sh.pool, masks, candidates);
                 // phase C: score and Metropolis decision
                 if (have) {
-                    const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
-                    const double new_score = overlap ? __longlong_as_double(0x7FF8000000000000ll)
-                                                     : (P.area * (double)P.n_syms) / cell_area;
+                    double new_score;
+                    if constexpr (KIND == CP_LJ) {
+                        new_score = lj_score;
+                    } else {
+                        const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
+                        new_score = overlap ? __longlong_as_double(0x7FF8000000000000ll)
+                                            : (P.area * (double)P.n_syms) / cell_area;
+                    }
                     const double threshold = rng_draw_threshold<RNG>(rng);
                     if (accept_move(new_score, score_current, kt, threshold)) {
                         score_current = new_score;

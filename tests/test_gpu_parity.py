@@ -259,13 +259,14 @@ def test_trajectories_against_glibc_oracle(eng):
             assert res[k].rejections == ores[k].rejections
 
 
-def test_lj_trajectories(eng):
+@pytest.mark.parametrize("lanes", [1, 8, 32])
+def test_lj_trajectories(eng, lanes):
     """BASELINE.json configs[3] (LJ trimer / circle): the energy sum keeps the reference's order, so
     whole trajectories are bit-identical as well (the contract only asks for 1e-6 relative)."""
     bopt = orc.build_optimiser(steps=600, inner_steps=200)
     for spec, group in ((("lj_trimer",), "p2"), (("lj_circle",), "p1"), (("lj_trimer", 0.63), "p2gg"),
                         (("lj_circle",), "p2mg")):
-        best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 16)
+        best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 16, lanes=lanes)
         for k in range(16):
             assert res[k].score == pytest.approx(ores[k].score, rel=LJ_RTOL)
             assert list(res[k].dof) == list(ores[k].dof) and res[k].score == ores[k].score, (spec, group, k)

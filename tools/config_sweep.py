@@ -18,7 +18,7 @@ cases = [
     ("C2 pentagon p2gg", cp.PackedState, cp.LineShape.polygon(5), "p2gg", 65536, {}),
     ("C3 trimer p2gg anneal", cp.PackedState, cp.MolecularShape2.from_trimer(0.637556, 120.0, 1.0), "p2gg", 262144,
      dict(kt_finish=0.001)),
-    ("C4 LJ trimer p2gg", cp.PotentialState, cp.LJShape2.from_trimer(0.637556, 120.0, 1.0), "p2gg", 16384, {}),
+    ("C4 LJ trimer p2gg", cp.PotentialState, cp.LJShape2.from_trimer(0.637556, 120.0, 1.0), "p2gg", 131072, {}),
     ("C4 LJ circle p1", cp.PotentialState, cp.LJShape2.circle(), "p1", 131072, {}),
     ("C5 triangle p1m1", cp.PackedState, cp.LineShape.polygon(3), "p1m1", 65536, {}),
     ("C5 12-gon p2gg", cp.PackedState, cp.LineShape.polygon(12), "p2gg", 65536, {}),

@@ -161,7 +161,9 @@ static int auto_lanes(const KProblem &k) {
     // Hard shapes: one thread per replica whenever the per-thread geometry fits in shared memory
     // (measured 4-5x faster than a warp per replica on B200, profiles/README.md).  LJ and very
     // large shapes: lane groups sized to the parallel work of one move.
-    if (cp_thread_kernel_fits(k)) return 1;
+    // at least two 64-thread blocks must fit an SM, else the warp-per-replica kernel is faster
+    // (12-gon in p2gg: 117 KB per block; measured with tools/lane_sweep.py)
+    if (cp_thread_kernel_fits(k) && cp_thread_shared_bytes(k) <= 110 * 1024) return 1;
     const int pair_tests = k.n_syms * (k.n_syms - 1) / 2 * k.n_items * k.n_items;
     const int cands = k.n_syms * k.n_syms * (k.kind == CP_LJ ? 48 : 8);
     const int work = pair_tests > cands ? pair_tests : cands;

@@ -6,6 +6,8 @@ bool cp_thread_kernel_fits(const KProblem &P) {
     return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms) <= 200 * 1024;
 }
 
+size_t cp_thread_shared_bytes(const KProblem &P) { return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms); }
+
 cudaError_t cp_launch_mc(const KParams &K, int lanes, cudaStream_t st) {
     switch (K.prob.kind) {
     case CP_POLYGON: return lanes == 1 ? cp_thread_polygon_mc(K, lanes, st) : cp_group_polygon_mc(K, lanes, st);

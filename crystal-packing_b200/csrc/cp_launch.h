@@ -15,6 +15,7 @@ cudaError_t cp_launch_replay(const KProblem &P, int lanes, const double *init, c
                              unsigned long long n_moves, unsigned long long n, cp_decision *out, cudaStream_t st);
 // does the per-thread geometry of this problem fit the one-thread-per-replica kernels?
 bool cp_thread_kernel_fits(const KProblem &P);
+size_t cp_thread_shared_bytes(const KProblem &P);
 
 // per-kind implementations (cp_group_<kind>.cu, cp_thread_<kind>.cu)
 #define CP_DECLARE_KIND(name)                                                                                  \

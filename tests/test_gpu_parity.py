@@ -274,6 +274,19 @@ def test_lj_trajectories(eng, lanes):
         assert best.best_replica == idx and best.best_score == obest.score
 
 
+@pytest.mark.parametrize("group", GROUPS)
+def test_c5_sweep_polygons_all_groups(eng, group):
+    """BASELINE.json configs[4]: 3..12-sided polygons x all seven plane groups, default kernel
+    selection, whole pipeline bit-identical to the oracle (few replicas, short schedule)."""
+    bopt = orc.build_optimiser(steps=300, inner_steps=100)
+    for sides in range(3, 13):
+        best, res, idx, obest, ores = run_both(eng, ("polygon", sides), group, bopt, 6)
+        for k in range(6):
+            assert list(res[k].dof) == list(ores[k].dof), (sides, group, k)
+            assert res[k].score == ores[k].score and res[k].rejections == ores[k].rejections
+        assert best.best_replica == idx
+
+
 def test_reference_integration_tests(eng):
     # crystal-packing/tests/packing.rs:14-52 and tests/potential.rs:14-52 through the mirrored API
     state = cp.PackedState.from_group(cp.LineShape.from_radial("Square", [1.0] * 4), "p2")

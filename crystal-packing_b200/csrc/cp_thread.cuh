@@ -19,7 +19,7 @@
 
 #include "cp_device.cuh"
 
-constexpr int kThreadBlock = 64;
+constexpr int kThreadBlock = 32;
 
 // doubles of shared memory each thread needs
 __host__ __device__ inline int thread_geo_doubles(int kind, int n_items, int n_syms) {
@@ -404,7 +404,7 @@ __device__ __forceinline__ ThreadShared thread_shared(double *smem, int kind, in
 // Semantics are those of mc_kernel in cp_api.cu: MCOptimiser::optimise_state (optimisation.rs:80-180)
 // for every stage, seeds and bounds per stage as analyse_state / generate_basis set them.
 template <int KIND, int NI, int RNG>
-__global__ void __launch_bounds__(kThreadBlock, 7) mc_thread_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
     const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);

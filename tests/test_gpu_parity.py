@@ -302,6 +302,54 @@ def test_reference_integration_tests(eng):
     assert final_lj.last_rejections == 691
 
 
+def test_per_replica_initial_states_and_split_calls(eng):
+    """cp_run with init_dof (each replica continues from its own state, as a resumed run would),
+    and cp_prepare + cp_launch + cp_fetch giving the same answer as cp_run."""
+    import random
+
+    rnd = random.Random(9)
+    cstate, ostate = make_states(("polygon", 5), "p2gg")
+    base = orc.get_dof(ostate)
+    inits = [[base[0] * rnd.uniform(0.7, 1.0), rnd.uniform(0.8, 1.0), base[2], rnd.uniform(-0.3, -0.2),
+              rnd.uniform(-0.3, -0.2), rnd.uniform(0.0, 0.3)] for _ in range(40)]
+    assert all(not math.isnan(v) for v in oracle_scores(ostate, inits))
+    sched = cp.MCOptimiser(0.05, 0.5, 0.01, 900, 300, 0, None).schedule
+    for lanes in (0, 32):
+        eng.set_lanes(lanes)
+        best, res = eng.run(cstate._problem, [sched], 40, replica_begin=100, rng=cp.RNG_PCG64MCG, init_dof=inits)
+        for k, init in enumerate(inits):
+            s = orc.clone(ostate)
+            orc.set_dof(s, init)
+            rc, _, rej = orc.optimise(s, 0.05, 0.5, 0.01, 900, 300, 100 + k)
+            assert rc == 0 and list(res[k].dof) == orc.get_dof(s) and res[k].rejections == rej
+            assert res[k].score == orc.score(s)
+        scores = [r.score for r in res]
+        assert best.replica == 100 + scores.index(max(scores)) and best.result.score == max(scores)
+    eng.set_lanes(0)
+    flat = (C.c_double * (6 * 40))(*[v for d in inits for v in d])
+    eng.prepare(cstate._problem, [sched], 40, replica_begin=100, rng=cp.RNG_PCG64MCG, init_dof_buffer=flat)
+    eng.launch()
+    out = (cp.capi.ReplicaResult * 40)()
+    best2 = eng.fetch(out)
+    assert [list(r.dof) for r in out] == [list(r.dof) for r in res] and best2.replica == best.replica
+    t = eng.timing()
+    assert t.launches == 3 and t.kernel_ms > 0 and t.lanes_per_replica == 1
+
+
+def test_million_replicas(eng):
+    """BASELINE.json configs[3]/[4] sizes: 1,048,576 replicas in one launch (short schedule)."""
+    state = cp.PackedState.from_group(cp.LineShape.polygon(4), "p1")
+    opts = cp.BuildOptimiser.cli_defaults(steps=50, inner_steps=50)
+    n = 1 << 20
+    eng.prepare(state._problem, opts.pipeline(), n, rng=cp.RNG_PHILOX)
+    eng.launch()
+    out = (cp.capi.ReplicaResult * n)()
+    best = eng.fetch(out)
+    assert all(out[i].moves == 200 for i in range(0, n, 4099)) and out[n - 1].moves == 200
+    assert 0.125 < best.result.score <= 1.0 and best.replica < n
+    assert out[best.replica].score == best.result.score
+
+
 def test_invalid_initial_state_is_an_error(eng):
     # optimisation.rs:81-84: panic!("Invalid configuration passed to function, exiting.")
     state = cp.PackedState.from_group(cp.LineShape.polygon(4), "p2")

@@ -447,8 +447,16 @@ __global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __gri
             for (;;) {
                 bool have = false;
                 int slot = 0;
-                double val = 0., new_val = 0.;
-                while (live && it < S.inner && !have) {  // draw until a proposal is in bounds
+                double val = 0., new_val = 0., threshold = 0., new_score = 0., new_s = 0., new_c = 0.;
+                // Draw until a proposal needs scoring.  Out-of-bounds proposals are rejected by
+                // Basis::set_value without a score (optimisation.rs:120-123).  For hard shapes the
+                // packing fraction depends on the cell DOFs only, so `Some(new_score)` is known
+                // before any overlap test: when the Metropolis rule would reject even a valid
+                // state (a cell move that lowers the score, lost against the threshold) the
+                // reference's answer is "rejected" whether check_intersection says None or Some,
+                // and the overlap test is skipped.  Draw order (index, step, threshold) and every
+                // decision are unchanged.
+                while (live && it < S.inner && !have) {
                     ++it;
                     int basis_index;
                     double sample;
@@ -459,24 +467,46 @@ __global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __gri
                     double lo, hi;
                     slot_bounds(slot, len0, ratio0, lo, hi);
                     have = lo <= new_val && new_val <= hi;
-                    if (!have) ++loop_rejections;
+                    if (!have) {
+                        ++loop_rejections;
+                        continue;
+                    }
+                    if constexpr (KIND != CP_LJ) {
+                        threshold = rng_draw_threshold<RNG>(rng);
+                        new_score = score_current;  // site moves leave the packing fraction as it is
+                        if (slot <= 2) {
+                            double sa_new = t.sa;
+                            if (slot == 2) {
+                                cp_sincos(new_val, &new_s, &new_c);
+                                sa_new = new_s;
+                            }
+                            const double len = slot == 0 ? new_val : d.v[0], ratio = slot == 1 ? new_val : d.v[1];
+                            const double cell_area = sa_new * len * (len * ratio);  // cell.rs:190-192
+                            new_score = (P.area * (double)P.n_syms) / cell_area;    // packed.rs:84
+                            have = accept_move(new_score, score_current, kt, threshold);
+                            if (!have) ++loop_rejections;
+                        }
+                    }
                 }
                 if (!__any_sync(0xffffffffu, have)) break;
                 // phase A (lanes holding a proposal): geometry and candidate generation
                 int candidates = 0;
-                double old_s = 0., old_c = 0., lj_score = 0.;
+                double old_s = 0., old_c = 0.;
                 const CellCache old_cc = cc;
                 if (have) {
                     d.set(slot, new_val);
-                    if (slot == 5 || slot == 2) {  // only these two DOFs enter sin/cos
-                        double s_, c_;
-                        cp_sincos(new_val, &s_, &c_);
-                        if (slot == 5) { old_s = t.st; old_c = t.ct; t.st = s_; t.ct = c_; }
-                        else { old_s = t.sa; old_c = t.ca; t.sa = s_; t.ca = c_; }
+                    if (slot == 5) {  // the site angle and the cell angle are the only DOFs inside sin/cos
+                        old_s = t.st; old_c = t.ct;
+                        cp_sincos(new_val, &t.st, &t.ct);
+                    }
+                    if (slot == 2) {
+                        old_s = t.sa; old_c = t.ca;
+                        if constexpr (KIND == CP_LJ) cp_sincos(new_val, &new_s, &new_c);
+                        t.sa = new_s; t.ca = new_c;
                     }
                     if (slot <= 2) cc = cell_cache_of(d);
                     if constexpr (KIND == CP_LJ) {
-                        lj_score = t_lj_score<NI>(P, g, d, t, cc);
+                        new_score = t_lj_score<NI>(P, g, d, t, cc);
                     } else {
                         t_build_geometry<KIND, NI>(P, g, d, t);
                         candidates = t_sweep<KIND, NI>(P, g, d, t, cc, masks);
@@ -485,18 +515,16 @@ __global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __gri
                 // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
                 bool overlap = false;
                 if constexpr (KIND != CP_LJ) overlap = t_drain_warp<KIND, NI>(P, smem, sh.pool, masks, candidates);
-                // phase C: score and Metropolis decision
+                // phase C: Metropolis decision
                 if (have) {
-                    double new_score;
+                    bool accepted;
                     if constexpr (KIND == CP_LJ) {
-                        new_score = lj_score;
+                        threshold = rng_draw_threshold<RNG>(rng);
+                        accepted = accept_move(new_score, score_current, kt, threshold);
                     } else {
-                        const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
-                        new_score = overlap ? __longlong_as_double(0x7FF8000000000000ll)
-                                            : (P.area * (double)P.n_syms) / cell_area;
+                        accepted = !overlap;  // the rule itself was evaluated before the overlap test
                     }
-                    const double threshold = rng_draw_threshold<RNG>(rng);
-                    if (accept_move(new_score, score_current, kt, threshold)) {
+                    if (accepted) {
                         score_current = new_score;
                     } else {
                         d.set(slot, val);

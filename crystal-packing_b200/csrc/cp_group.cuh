@@ -95,17 +95,49 @@ __global__ void __launch_bounds__(kBlock) mc_kernel(const __grid_constant__ KPar
                     ++loop_rejections;
                     continue;
                 }
+                // For hard shapes Some(new_score) depends on the cell DOFs only, so the Metropolis
+                // rule can be evaluated before the overlap test; when it would reject even a valid
+                // state the answer is "rejected" whatever check_intersection returns, and the test
+                // is skipped.  Draw order and every decision are unchanged (see cp_thread.cuh).
+                double threshold = 0., s_ = 0., c_ = 0., known_score = score_current;
+                bool prechecked = false;
+                if (KIND != CP_LJ) {
+                    threshold = rng_draw_threshold<RNG>(rng);
+                    prechecked = true;
+                    if (slot <= 2) {
+                        double sa_new = trig.sa;
+                        if (slot == 2) {
+                            cp_sincos(new_val, &s_, &c_);
+                            sa_new = s_;
+                        }
+                        const double len = slot == 0 ? new_val : d.v[0], ratio = slot == 1 ? new_val : d.v[1];
+                        known_score = (P.area * (double)P.n_syms) / (sa_new * len * (len * ratio));
+                        if (!accept_move(known_score, score_current, kt, threshold)) {
+                            ++loop_rejections;
+                            continue;
+                        }
+                    }
+                }
                 d.set(slot, new_val);
                 double old_s = 0., old_c = 0.;
-                if (slot == 5 || slot == 2) {  // the only DOFs that enter sin/cos
-                    double s_, c_;
-                    cp_sincos(new_val, &s_, &c_);
-                    if (slot == 5) { old_s = trig.st; old_c = trig.ct; trig.st = s_; trig.ct = c_; }
-                    else { old_s = trig.sa; old_c = trig.ca; trig.sa = s_; trig.ca = c_; }
+                if (slot == 5) {  // the only DOFs that enter sin/cos are the site and cell angles
+                    old_s = trig.st; old_c = trig.ct;
+                    cp_sincos(new_val, &trig.st, &trig.ct);
+                }
+                if (slot == 2) {
+                    old_s = trig.sa; old_c = trig.ca;
+                    if (KIND == CP_LJ) cp_sincos(new_val, &s_, &c_);
+                    trig.sa = s_; trig.ca = c_;
                 }
                 const double new_score = state_score<KIND, L>(P, s_items, s_shift, g, d, trig, gmask, lane);
-                const double threshold = rng_draw_threshold<RNG>(rng);
-                if (accept_move(new_score, score_current, kt, threshold)) {
+                bool accepted;
+                if (prechecked) {
+                    accepted = new_score == new_score;  // Some(_): the rule itself already said yes
+                } else {
+                    threshold = rng_draw_threshold<RNG>(rng);
+                    accepted = accept_move(new_score, score_current, kt, threshold);
+                }
+                if (accepted) {
                     score_current = new_score;
                 } else {
                     d.set(slot, val);

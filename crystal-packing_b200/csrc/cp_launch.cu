@@ -8,42 +8,76 @@ bool cp_thread_kernel_fits(const KProblem &P) {
 
 size_t cp_thread_shared_bytes(const KProblem &P) { return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms); }
 
+// one thread per replica: pick the build specialised for this component count, if there is one
+#define CP_THREAD_ROUTE(WHAT, n_items, ...)                                                      \
+    switch (kind) {                                                                              \
+    case CP_POLYGON:                                                                             \
+        switch (n_items) {                                                                       \
+        case 3: return cp_thread_polygon_##WHAT##_3(__VA_ARGS__);                                \
+        case 4: return cp_thread_polygon_##WHAT##_4(__VA_ARGS__);                                \
+        case 5: return cp_thread_polygon_##WHAT##_5(__VA_ARGS__);                                \
+        case 6: return cp_thread_polygon_##WHAT##_6(__VA_ARGS__);                                \
+        default: return cp_thread_polygon_##WHAT##_0(__VA_ARGS__);                               \
+        }                                                                                        \
+    case CP_DISCS:                                                                               \
+        switch (n_items) {                                                                       \
+        case 1: return cp_thread_discs_##WHAT##_1(__VA_ARGS__);                                  \
+        case 3: return cp_thread_discs_##WHAT##_3(__VA_ARGS__);                                  \
+        default: return cp_thread_discs_##WHAT##_0(__VA_ARGS__);                                 \
+        }                                                                                        \
+    case CP_LJ:                                                                                  \
+        switch (n_items) {                                                                       \
+        case 1: return cp_thread_lj_##WHAT##_1(__VA_ARGS__);                                     \
+        case 3: return cp_thread_lj_##WHAT##_3(__VA_ARGS__);                                     \
+        default: return cp_thread_lj_##WHAT##_0(__VA_ARGS__);                                    \
+        }                                                                                        \
+    default: return cudaErrorInvalidValue;                                                       \
+    }
+
+static cudaError_t thread_route_mc(const KParams &K, cudaStream_t st) {
+    const int kind = K.prob.kind;
+    CP_THREAD_ROUTE(mc, K.prob.n_items, K, st)
+}
+static cudaError_t thread_route_score(const KProblem &P, const double *dof, unsigned long long n, double *out,
+                                      cudaStream_t st) {
+    const int kind = P.kind;
+    CP_THREAD_ROUTE(score, P.n_items, P, dof, n, out, st)
+}
+static cudaError_t thread_route_replay(const KProblem &P, const double *init, const cp_move *mv,
+                                       unsigned long long n_moves, unsigned long long n, cp_decision *out,
+                                       cudaStream_t st) {
+    const int kind = P.kind;
+    CP_THREAD_ROUTE(replay, P.n_items, P, init, mv, n_moves, n, out, st)
+}
+
 cudaError_t cp_launch_mc(const KParams &K, int lanes, cudaStream_t st) {
+    if (lanes == 1) return thread_route_mc(K, st);
     switch (K.prob.kind) {
-    case CP_POLYGON: return lanes == 1 ? cp_thread_polygon_mc(K, lanes, st) : cp_group_polygon_mc(K, lanes, st);
-    case CP_DISCS: return lanes == 1 ? cp_thread_discs_mc(K, lanes, st) : cp_group_discs_mc(K, lanes, st);
-    case CP_LJ: return lanes == 1 ? cp_thread_lj_mc(K, lanes, st) : cp_group_lj_mc(K, lanes, st);
+    case CP_POLYGON: return cp_group_polygon_mc(K, lanes, st);
+    case CP_DISCS: return cp_group_discs_mc(K, lanes, st);
+    case CP_LJ: return cp_group_lj_mc(K, lanes, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t cp_launch_score(const KProblem &P, int lanes, const double *dof, unsigned long long n, double *out,
                             cudaStream_t st) {
+    if (lanes == 1) return thread_route_score(P, dof, n, out, st);
     switch (P.kind) {
-    case CP_POLYGON:
-        return lanes == 1 ? cp_thread_polygon_score(P, lanes, dof, n, out, st)
-                          : cp_group_polygon_score(P, lanes, dof, n, out, st);
-    case CP_DISCS:
-        return lanes == 1 ? cp_thread_discs_score(P, lanes, dof, n, out, st)
-                          : cp_group_discs_score(P, lanes, dof, n, out, st);
-    case CP_LJ:
-        return lanes == 1 ? cp_thread_lj_score(P, lanes, dof, n, out, st) : cp_group_lj_score(P, lanes, dof, n, out, st);
+    case CP_POLYGON: return cp_group_polygon_score(P, lanes, dof, n, out, st);
+    case CP_DISCS: return cp_group_discs_score(P, lanes, dof, n, out, st);
+    case CP_LJ: return cp_group_lj_score(P, lanes, dof, n, out, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t cp_launch_replay(const KProblem &P, int lanes, const double *init, const cp_move *mv,
                              unsigned long long n_moves, unsigned long long n, cp_decision *out, cudaStream_t st) {
+    if (lanes == 1) return thread_route_replay(P, init, mv, n_moves, n, out, st);
     switch (P.kind) {
-    case CP_POLYGON:
-        return lanes == 1 ? cp_thread_polygon_replay(P, lanes, init, mv, n_moves, n, out, st)
-                          : cp_group_polygon_replay(P, lanes, init, mv, n_moves, n, out, st);
-    case CP_DISCS:
-        return lanes == 1 ? cp_thread_discs_replay(P, lanes, init, mv, n_moves, n, out, st)
-                          : cp_group_discs_replay(P, lanes, init, mv, n_moves, n, out, st);
-    case CP_LJ:
-        return lanes == 1 ? cp_thread_lj_replay(P, lanes, init, mv, n_moves, n, out, st)
-                          : cp_group_lj_replay(P, lanes, init, mv, n_moves, n, out, st);
+    case CP_POLYGON: return cp_group_polygon_replay(P, lanes, init, mv, n_moves, n, out, st);
+    case CP_DISCS: return cp_group_discs_replay(P, lanes, init, mv, n_moves, n, out, st);
+    case CP_LJ: return cp_group_lj_replay(P, lanes, init, mv, n_moves, n, out, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -28,9 +28,24 @@ size_t cp_thread_shared_bytes(const KProblem &P);
 CP_DECLARE_KIND(group_polygon)
 CP_DECLARE_KIND(group_discs)
 CP_DECLARE_KIND(group_lj)
-CP_DECLARE_KIND(thread_polygon)
-CP_DECLARE_KIND(thread_discs)
-CP_DECLARE_KIND(thread_lj)
+#define CP_DECLARE_THREAD_NI(name, NI)                                                                          \
+    cudaError_t cp_##name##_mc_##NI(const KParams &K, cudaStream_t st);                                         \
+    cudaError_t cp_##name##_score_##NI(const KProblem &P, const double *dof, unsigned long long n, double *out, \
+                                       cudaStream_t st);                                                       \
+    cudaError_t cp_##name##_replay_##NI(const KProblem &P, const double *init, const cp_move *mv,               \
+                                        unsigned long long n_moves, unsigned long long n, cp_decision *out,    \
+                                        cudaStream_t st);
+CP_DECLARE_THREAD_NI(thread_polygon, 0)
+CP_DECLARE_THREAD_NI(thread_polygon, 3)
+CP_DECLARE_THREAD_NI(thread_polygon, 4)
+CP_DECLARE_THREAD_NI(thread_polygon, 5)
+CP_DECLARE_THREAD_NI(thread_polygon, 6)
+CP_DECLARE_THREAD_NI(thread_discs, 0)
+CP_DECLARE_THREAD_NI(thread_discs, 1)
+CP_DECLARE_THREAD_NI(thread_discs, 3)
+CP_DECLARE_THREAD_NI(thread_lj, 0)
+CP_DECLARE_THREAD_NI(thread_lj, 1)
+CP_DECLARE_THREAD_NI(thread_lj, 3)
 
 // dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
 template <typename Kernel>

@@ -44,23 +44,16 @@ static cudaError_t thread_replay(const KProblem &P, const double *init, const cp
     return cudaGetLastError();
 }
 
-// NA, NB: the two specialised component counts of this kind; anything else runs the NI = 0 build
-#define CP_DEFINE_THREAD_KIND(KIND, name, NA, NB)                                                              \
-    cudaError_t cp_##name##_mc(const KParams &K, int, cudaStream_t st) {                                       \
-        if (K.prob.n_items == NA) return thread_mc<KIND, NA>(K, st);                                           \
-        if (K.prob.n_items == NB) return thread_mc<KIND, NB>(K, st);                                           \
-        return thread_mc<KIND, 0>(K, st);                                                                      \
+// Defines the three entry points of one (kind, component count) pair.  Suffix = the count, or 0
+// for the run-time-count build.
+#define CP_DEFINE_THREAD_NI(KIND, name, NI)                                                                    \
+    cudaError_t cp_##name##_mc_##NI(const KParams &K, cudaStream_t st) { return thread_mc<KIND, NI>(K, st); }   \
+    cudaError_t cp_##name##_score_##NI(const KProblem &P, const double *dof, unsigned long long n, double *out, \
+                                       cudaStream_t st) {                                                      \
+        return thread_score<KIND, NI>(P, dof, n, out, st);                                                     \
     }                                                                                                          \
-    cudaError_t cp_##name##_score(const KProblem &P, int, const double *dof, unsigned long long n, double *out, \
-                                  cudaStream_t st) {                                                           \
-        if (P.n_items == NA) return thread_score<KIND, NA>(P, dof, n, out, st);                                \
-        if (P.n_items == NB) return thread_score<KIND, NB>(P, dof, n, out, st);                                \
-        return thread_score<KIND, 0>(P, dof, n, out, st);                                                      \
-    }                                                                                                          \
-    cudaError_t cp_##name##_replay(const KProblem &P, int, const double *init, const cp_move *mv,              \
-                                   unsigned long long n_moves, unsigned long long n, cp_decision *out,         \
-                                   cudaStream_t st) {                                                          \
-        if (P.n_items == NA) return thread_replay<KIND, NA>(P, init, mv, n_moves, n, out, st);                 \
-        if (P.n_items == NB) return thread_replay<KIND, NB>(P, init, mv, n_moves, n, out, st);                 \
-        return thread_replay<KIND, 0>(P, init, mv, n_moves, n, out, st);                                       \
+    cudaError_t cp_##name##_replay_##NI(const KProblem &P, const double *init, const cp_move *mv,               \
+                                        unsigned long long n_moves, unsigned long long n, cp_decision *out,    \
+                                        cudaStream_t st) {                                                     \
+        return thread_replay<KIND, NI>(P, init, mv, n_moves, n, out, st);                                      \
     }

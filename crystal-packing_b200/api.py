@@ -111,6 +111,12 @@ class LJShape2(_Shape):
         return cls("circle", p)
 
 
+def refresh_shape(shape):
+    """Recompute area() and enclosing_radius() after the items were edited by hand."""
+    _check(load_library().cp_shape_finish(C.byref(shape._problem)))
+    return shape
+
+
 # ---------------------------------------------------------------------------------------- symmetry
 class Transform2:
     """Rows 0-1 of a symmetry operator (Transform2::from_operations, transform.rs:124-183)."""
@@ -134,7 +140,27 @@ class WallpaperGroup:
     @property
     def name(self):
         # the reference labels p1g1 as "p1m1" (wallpaper.rs:154-158)
+        if self.key is None:
+            return getattr(self, "custom_name", "custom")
         return "p1m1" if self.key in ("p1g1", "pg") else self.key
+
+
+_FAMILY_NAMES = {"Monoclinic": capi.CP_MONOCLINIC, "Orthorhombic": capi.CP_ORTHORHOMBIC,
+                 "Hexagonal": capi.CP_HEXAGONAL, "Tetragonal": capi.CP_TETRAGONAL}
+
+
+def group_from_symmetries(name, family, matrices):
+    """WallpaperGroup from serialised data: `matrices` are 3x3 column-major lists (the serde form of
+    Transform2).  Matches the built-in table when it can (so `key` round-trips), else keeps the
+    operators as given."""
+    rows = [[m[0], m[3], m[6], m[1], m[4], m[7]] for m in matrices]
+    for key in ("p1", "p2", "p1m1", "p1g1", "p2mm", "p2mg", "p2gg"):
+        g = WallpaperGroups.from_str(key)
+        if g.symmetries == rows and g.name == name:
+            return g
+    g = WallpaperGroup(None, _FAMILY_NAMES[family], rows)
+    g.custom_name = name
+    return g
 
 
 class WallpaperGroups:
@@ -296,7 +322,13 @@ class _State:
             group = WallpaperGroups.from_str(group)
         p = capi.Problem()
         C.memmove(C.byref(p), C.byref(shape._problem), C.sizeof(capi.Problem))
-        _check(load_library().cp_problem_from_group(C.byref(p), group.key.encode()))
+        if group.key is None:  # operators given explicitly (deserialised state); DOFs are set by the caller
+            p.family, p.n_syms = group.family, len(group.symmetries)
+            for s_, row in enumerate(group.symmetries):
+                for c_, v in enumerate(row):
+                    p.syms[s_][c_] = v
+        else:
+            _check(load_library().cp_problem_from_group(C.byref(p), group.key.encode()))
         return cls(shape, group, p)
 
     def clone(self):
@@ -336,6 +368,18 @@ class _State:
 
     def __lt__(self, other):  # Ord by score (packed.rs:49-68)
         return self.score() < other.score()
+
+    def to_json(self):
+        """serde_json::to_string(&state) (main.rs:263); see serialise.py for the layout."""
+        from .serialise import state_to_json
+
+        return state_to_json(self)
+
+    @classmethod
+    def from_json(cls, text):
+        from .serialise import state_from_json
+
+        return state_from_json(text, cls, cls.shape_types)
 
 
 class PackedState(_State):

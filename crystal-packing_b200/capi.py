@@ -106,6 +106,7 @@ SIGNATURES = {
     "cp_shape_polygon": (_i, [_P(_d), _i, _P(Problem)]),
     "cp_shape_trimer": (_i, [_i, _d, _d, _d, _P(Problem)]),
     "cp_shape_circle": (_i, [_i, _P(Problem)]),
+    "cp_shape_finish": (_i, [_P(Problem)]),
     "cp_parse_operations": (_i, [C.c_char_p, _P(_d)]),
     "cp_group_lookup": (_i, [C.c_char_p, _P(C.c_int32), _P(C.c_int32), _P((_d * 6) * MAX_SYMS)]),
     "cp_problem_from_group": (_i, [_P(Problem), C.c_char_p]),

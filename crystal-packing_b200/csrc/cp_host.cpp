@@ -169,6 +169,14 @@ cp_status cp_shape_circle(int kind, cp_problem *out) {
     return CP_OK;
 }
 
+cp_status cp_shape_finish(cp_problem *shape) {
+    if (!shape) return cp_fail(CP_ERR_INVALID_ARG, "cp_shape_finish: null shape");
+    if (shape->kind < CP_POLYGON || shape->kind > CP_LJ || shape->n_items < 1 || shape->n_items > CP_MAX_ITEMS)
+        return cp_fail(CP_ERR_INVALID_ARG, "cp_shape_finish: kind / n_items out of range");
+    finish_shape(shape);
+    return CP_OK;
+}
+
 cp_status cp_parse_operations(const char *sym_ops, double out[6]) {
     // Transform2::from_operations (transform.rs:124-183).  Quirks kept: single digits only, '*'
     // behaves like '/', a constant's sign comes from the last '-' seen.

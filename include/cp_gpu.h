@@ -159,6 +159,9 @@ cp_status cp_shape_polygon(const double *radii, int n, cp_problem *out);
 cp_status cp_shape_trimer(int kind, double radius, double angle, double distance, cp_problem *out);
 /* MolecularShape2::circle / LJShape2::circle (molecular_shape2.rs:167-172, lj_shape.rs:146-151) */
 cp_status cp_shape_circle(int kind, cp_problem *out);
+/* Shape::area / Shape::enclosing_radius (line_shape.rs:60-72,86-93, molecular_shape2.rs:39-52,66-74,
+ * lj_shape.rs:52-60) recomputed from `items` — for shapes filled in by hand or read from JSON */
+cp_status cp_shape_finish(cp_problem *shape);
 /* Transform2::from_operations (transform.rs:124-183): rows 0-1 of the operator */
 cp_status cp_parse_operations(const char *sym_ops, double out[6]);
 /* WallpaperGroups::from_str + TryFrom (wallpaper.rs:100-110,134-176) */

@@ -432,18 +432,47 @@ __global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __gri
     Rng rng;
     CellCache cc = cell_cache_of(d);
     CandMasks masks = sh.m;
-    for (int stage = 0; stage < K.n_stages; ++stage) {
-        const KStage S = K.stages[stage];
-        const double len0 = d.v[0], ratio0 = d.v[1];
+    // Every lane walks its own (stage, outer loop, inner step) schedule: replicas of one warp need
+    // different numbers of scored proposals per inner loop (the in-bounds fraction depends on the
+    // replica's cell), and synchronising at loop ends would leave the faster lanes idle there.  Only
+    // the score phases below are warp-wide.
+    int stage = 0;
+    bool done = !alive;
+    KStage S = K.stages[0];
+    double len0 = d.v[0], ratio0 = d.v[1], kt = 0., step_ratio = 1.0, score_start = score_current;
+    int convergence_count = 0;
+    unsigned long long outer = 0, loop = 1, it = 0, loop_rejections = 0;
+    auto begin_stage = [&]() {
+        S = K.stages[stage];
+        len0 = d.v[0];  // generate_basis(): bounds captured per optimise_state call (cell.rs:139-152)
+        ratio0 = d.v[1];
         rng_begin_stage<RNG>(rng, K.seed_base + replica, replica, n_basis);
-        double kt = S.kt_start, step_ratio = 1.0;
-        int convergence_count = 0;
-        bool converged = false;
-        const unsigned long long outer = S.inner ? S.steps / S.inner : 0ull;
-        for (unsigned long long loop = 1; loop <= outer; ++loop) {
-            const bool live = alive && !converged;
-            const double score_start = score_current;
-            unsigned long long loop_rejections = 0, it = 0;
+        kt = S.kt_start;
+        step_ratio = 1.0;
+        convergence_count = 0;
+        outer = S.inner ? S.steps / S.inner : 0ull;
+        loop = 1;
+        it = 0;
+        loop_rejections = 0;
+        score_start = score_current;
+    };
+    auto next_stage = [&]() {  // skips stages that run no move (steps < inner_steps cannot happen after build())
+        for (;;) {
+            ++stage;
+            if (stage >= K.n_stages) {
+                done = true;
+                return;
+            }
+            begin_stage();
+            if (outer > 0) return;
+        }
+    };
+    if (!done) {
+        stage = -1;
+        next_stage();
+    }
+    {
+        {
             for (;;) {
                 bool have = false;
                 int slot = 0;
@@ -456,7 +485,28 @@ __global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __gri
                 // reference's answer is "rejected" whether check_intersection says None or Some,
                 // and the overlap test is skipped.  Draw order (index, step, threshold) and every
                 // decision are unchanged.
-                while (live && it < S.inner && !have) {
+                while (!done && !have) {
+                    if (it == S.inner) {  // end of an inner loop (optimisation.rs:138-167)
+                        moves += S.inner;
+                        rejections += loop_rejections;
+                        kt *= S.kt_ratio;
+                        bool converged = false;
+                        if (S.convergence == S.convergence) {
+                            if (score_current - score_start < S.convergence) {
+                                if (++convergence_count > 5) converged = true;
+                            } else {
+                                convergence_count = 0;
+                            }
+                        }
+                        if (!converged && step_ratio > 1e-4)
+                            step_ratio *= (double)S.inner / ((double)loop_rejections + 1.);
+                        ++loop;
+                        it = 0;
+                        loop_rejections = 0;
+                        score_start = score_current;
+                        if (converged || loop > outer) next_stage();
+                        continue;
+                    }
                     ++it;
                     int basis_index;
                     double sample;
@@ -534,20 +584,6 @@ __global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __gri
                         ++loop_rejections;
                     }
                 }
-            }
-            if (live) {
-                moves += S.inner;
-                rejections += loop_rejections;
-                kt *= S.kt_ratio;
-                if (S.convergence == S.convergence) {
-                    if (score_current - score_start < S.convergence) {
-                        if (++convergence_count > 5) converged = true;
-                    } else {
-                        convergence_count = 0;
-                    }
-                }
-                if (!converged && step_ratio > 1e-4)
-                    step_ratio *= (double)S.inner / ((double)loop_rejections + 1.);
             }
         }
     }

@@ -1,18 +1,21 @@
-// cp_thread.cuh — one THREAD per replica (lanes_per_replica = 1).
+// cp_thread.cuh — one THREAD per replica (lanes_per_replica = 1), the default kernels.
 //
-// The group kernels of cp_api.cu spread one replica over L lanes; profiling them on B200
-// (profiles/r1_base_*.txt) showed ~75 % of the issued instructions were replicated scalar work
-// (RNG, trigonometry, index arithmetic) and votes.  Here every lane owns a whole replica, so all of
-// that is useful work, and the sweeps of one replica run as straight-line loops with the
+// The group kernels (cp_group.cuh) spread one replica over L lanes; profiling them on B200
+// (profiles/r1_a_group32_first.txt) showed ~75 % of the issued instructions were replicated scalar
+// work (RNG, trigonometry, index arithmetic) and votes.  Here every lane owns a whole replica, so
+// all of that is useful work, and the sweeps of one replica run as straight-line loops with the
 // instruction-level parallelism of 25+ independent predicate evaluations.  What SIMT needs in
-// return is warp-uniform control flow, which the move loop below provides:
-//   * proposals are drawn in a short divergent loop until each lane holds an in-bounds one (the
-//     37 % of out-of-bounds proposals cost a draw, not a score slot), then all lanes score together;
-//   * periodic-image candidates that pass the distance filter are queued per lane and drained
-//     afterwards, so the expensive component tests run once per queued candidate instead of once
-//     per candidate index that any lane of the warp happens to pass.
-// Per-thread geometry lives in shared memory as [element][thread] (bank-conflict free).
-//
+// return is warp-uniform control flow around the expensive parts, which the move loop provides:
+//   * every lane walks its own (stage, outer loop, inner step) schedule and draws proposals in a
+//     short divergent loop until it holds one that needs scoring: out-of-bounds proposals cost a
+//     draw, and for hard shapes a cell move that the Metropolis rule rejects even if valid is
+//     rejected there too, before any overlap test (the packing fraction depends on the cell only);
+//   * phase A, per lane: geometry into shared memory ([element][thread], conflict-free) and the
+//     exactly pruned sweep over the periodic images; candidates become bits of one 64-bit word per
+//     ordered shape pair;
+//   * phase B, whole warp: the candidates of all 32 replicas are tested in rounds from a shared
+//     pool of 32 entries, one entry per lane, replicas dropping out at their first hit;
+//   * phase C, per lane: the decision.
 // Arithmetic is the same as cp_device.cuh: reference expression order, f64, no contraction.
 #ifndef CP_THREAD_CUH
 #define CP_THREAD_CUH
@@ -471,119 +474,115 @@ __global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __gri
         stage = -1;
         next_stage();
     }
-    {
-        {
-            for (;;) {
-                bool have = false;
-                int slot = 0;
-                double val = 0., new_val = 0., threshold = 0., new_score = 0., new_s = 0., new_c = 0.;
-                // Draw until a proposal needs scoring.  Out-of-bounds proposals are rejected by
-                // Basis::set_value without a score (optimisation.rs:120-123).  For hard shapes the
-                // packing fraction depends on the cell DOFs only, so `Some(new_score)` is known
-                // before any overlap test: when the Metropolis rule would reject even a valid
-                // state (a cell move that lowers the score, lost against the threshold) the
-                // reference's answer is "rejected" whether check_intersection says None or Some,
-                // and the overlap test is skipped.  Draw order (index, step, threshold) and every
-                // decision are unchanged.
-                while (!done && !have) {
-                    if (it == S.inner) {  // end of an inner loop (optimisation.rs:138-167)
-                        moves += S.inner;
-                        rejections += loop_rejections;
-                        kt *= S.kt_ratio;
-                        bool converged = false;
-                        if (S.convergence == S.convergence) {
-                            if (score_current - score_start < S.convergence) {
-                                if (++convergence_count > 5) converged = true;
-                            } else {
-                                convergence_count = 0;
-                            }
-                        }
-                        if (!converged && step_ratio > 1e-4)
-                            step_ratio *= (double)S.inner / ((double)loop_rejections + 1.);
-                        ++loop;
-                        it = 0;
-                        loop_rejections = 0;
-                        score_start = score_current;
-                        if (converged || loop > outer) next_stage();
-                        continue;
-                    }
-                    ++it;
-                    int basis_index;
-                    double sample;
-                    rng_draw_move<RNG>(rng, basis_index, sample);
-                    slot = basis_to_slot(basis_index, n_cell);
-                    val = d.get(slot);
-                    new_val = val + S.max_step * step_ratio * sample;
-                    double lo, hi;
-                    slot_bounds(slot, len0, ratio0, lo, hi);
-                    have = lo <= new_val && new_val <= hi;
-                    if (!have) {
-                        ++loop_rejections;
-                        continue;
-                    }
-                    if constexpr (KIND != CP_LJ) {
-                        threshold = rng_draw_threshold<RNG>(rng);
-                        new_score = score_current;  // site moves leave the packing fraction as it is
-                        if (slot <= 2) {
-                            double sa_new = t.sa;
-                            if (slot == 2) {
-                                cp_sincos(new_val, &new_s, &new_c);
-                                sa_new = new_s;
-                            }
-                            const double len = slot == 0 ? new_val : d.v[0], ratio = slot == 1 ? new_val : d.v[1];
-                            const double cell_area = sa_new * len * (len * ratio);  // cell.rs:190-192
-                            new_score = (P.area * (double)P.n_syms) / cell_area;    // packed.rs:84
-                            have = accept_move(new_score, score_current, kt, threshold);
-                            if (!have) ++loop_rejections;
-                        }
+    for (;;) {
+        bool have = false;
+        int slot = 0;
+        double val = 0., new_val = 0., threshold = 0., new_score = 0., new_s = 0., new_c = 0.;
+        // Draw until a proposal needs scoring.  Out-of-bounds proposals are rejected by
+        // Basis::set_value without a score (optimisation.rs:120-123).  For hard shapes the
+        // packing fraction depends on the cell DOFs only, so `Some(new_score)` is known
+        // before any overlap test: when the Metropolis rule would reject even a valid
+        // state (a cell move that lowers the score, lost against the threshold) the
+        // reference's answer is "rejected" whether check_intersection says None or Some,
+        // and the overlap test is skipped.  Draw order (index, step, threshold) and every
+        // decision are unchanged.
+        while (!done && !have) {
+            if (it == S.inner) {  // end of an inner loop (optimisation.rs:138-167)
+                moves += S.inner;
+                rejections += loop_rejections;
+                kt *= S.kt_ratio;
+                bool converged = false;
+                if (S.convergence == S.convergence) {
+                    if (score_current - score_start < S.convergence) {
+                        if (++convergence_count > 5) converged = true;
+                    } else {
+                        convergence_count = 0;
                     }
                 }
-                if (!__any_sync(0xffffffffu, have)) break;
-                // phase A (lanes holding a proposal): geometry and candidate generation
-                int candidates = 0;
-                double old_s = 0., old_c = 0.;
-                const CellCache old_cc = cc;
-                if (have) {
-                    d.set(slot, new_val);
-                    if (slot == 5) {  // the site angle and the cell angle are the only DOFs inside sin/cos
-                        old_s = t.st; old_c = t.ct;
-                        cp_sincos(new_val, &t.st, &t.ct);
-                    }
+                if (!converged && step_ratio > 1e-4)
+                    step_ratio *= (double)S.inner / ((double)loop_rejections + 1.);
+                ++loop;
+                it = 0;
+                loop_rejections = 0;
+                score_start = score_current;
+                if (converged || loop > outer) next_stage();
+                continue;
+            }
+            ++it;
+            int basis_index;
+            double sample;
+            rng_draw_move<RNG>(rng, basis_index, sample);
+            slot = basis_to_slot(basis_index, n_cell);
+            val = d.get(slot);
+            new_val = val + S.max_step * step_ratio * sample;
+            double lo, hi;
+            slot_bounds(slot, len0, ratio0, lo, hi);
+            have = lo <= new_val && new_val <= hi;
+            if (!have) {
+                ++loop_rejections;
+                continue;
+            }
+            if constexpr (KIND != CP_LJ) {
+                threshold = rng_draw_threshold<RNG>(rng);
+                new_score = score_current;  // site moves leave the packing fraction as it is
+                if (slot <= 2) {
+                    double sa_new = t.sa;
                     if (slot == 2) {
-                        old_s = t.sa; old_c = t.ca;
-                        if constexpr (KIND == CP_LJ) cp_sincos(new_val, &new_s, &new_c);
-                        t.sa = new_s; t.ca = new_c;
+                        cp_sincos(new_val, &new_s, &new_c);
+                        sa_new = new_s;
                     }
-                    if (slot <= 2) cc = cell_cache_of(d);
-                    if constexpr (KIND == CP_LJ) {
-                        new_score = t_lj_score<NI>(P, g, d, t, cc);
-                    } else {
-                        t_build_geometry<KIND, NI>(P, g, d, t);
-                        candidates = t_sweep<KIND, NI>(P, g, d, t, cc, masks);
-                    }
+                    const double len = slot == 0 ? new_val : d.v[0], ratio = slot == 1 ? new_val : d.v[1];
+                    const double cell_area = sa_new * len * (len * ratio);  // cell.rs:190-192
+                    new_score = (P.area * (double)P.n_syms) / cell_area;    // packed.rs:84
+                    have = accept_move(new_score, score_current, kt, threshold);
+                    if (!have) ++loop_rejections;
                 }
-                // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
-                bool overlap = false;
-                if constexpr (KIND != CP_LJ) overlap = t_drain_warp<KIND, NI>(P, smem, sh.pool, masks, candidates);
-                // phase C: Metropolis decision
-                if (have) {
-                    bool accepted;
-                    if constexpr (KIND == CP_LJ) {
-                        threshold = rng_draw_threshold<RNG>(rng);
-                        accepted = accept_move(new_score, score_current, kt, threshold);
-                    } else {
-                        accepted = !overlap;  // the rule itself was evaluated before the overlap test
-                    }
-                    if (accepted) {
-                        score_current = new_score;
-                    } else {
-                        d.set(slot, val);
-                        if (slot == 5) { t.st = old_s; t.ct = old_c; }
-                        if (slot == 2) { t.sa = old_s; t.ca = old_c; }
-                        cc = old_cc;
-                        ++loop_rejections;
-                    }
-                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        // phase A (lanes holding a proposal): geometry and candidate generation
+        int candidates = 0;
+        double old_s = 0., old_c = 0.;
+        const CellCache old_cc = cc;
+        if (have) {
+            d.set(slot, new_val);
+            if (slot == 5) {  // the site angle and the cell angle are the only DOFs inside sin/cos
+                old_s = t.st; old_c = t.ct;
+                cp_sincos(new_val, &t.st, &t.ct);
+            }
+            if (slot == 2) {
+                old_s = t.sa; old_c = t.ca;
+                if constexpr (KIND == CP_LJ) cp_sincos(new_val, &new_s, &new_c);
+                t.sa = new_s; t.ca = new_c;
+            }
+            if (slot <= 2) cc = cell_cache_of(d);
+            if constexpr (KIND == CP_LJ) {
+                new_score = t_lj_score<NI>(P, g, d, t, cc);
+            } else {
+                t_build_geometry<KIND, NI>(P, g, d, t);
+                candidates = t_sweep<KIND, NI>(P, g, d, t, cc, masks);
+            }
+        }
+        // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
+        bool overlap = false;
+        if constexpr (KIND != CP_LJ) overlap = t_drain_warp<KIND, NI>(P, smem, sh.pool, masks, candidates);
+        // phase C: Metropolis decision
+        if (have) {
+            bool accepted;
+            if constexpr (KIND == CP_LJ) {
+                threshold = rng_draw_threshold<RNG>(rng);
+                accepted = accept_move(new_score, score_current, kt, threshold);
+            } else {
+                accepted = !overlap;  // the rule itself was evaluated before the overlap test
+            }
+            if (accepted) {
+                score_current = new_score;
+            } else {
+                d.set(slot, val);
+                if (slot == 5) { t.st = old_s; t.ct = old_c; }
+                if (slot == 2) { t.sa = old_s; t.ca = old_c; }
+                cc = old_cc;
+                ++loop_rejections;
             }
         }
     }

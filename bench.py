@@ -325,7 +325,7 @@ def run_b200(args, rank, local_rank, world):
                 "traffic": 410368, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
                                                    "(profiles/r1_d_thread_final.txt); algorithmic HBM bytes are the 4.7 MB of results",
                 "peak_source": "measured here: FP64 FMA chains, 2 flops/FMA (MEASURED_PEAKS.json has no FP64 entry)",
-                "fp32_fma_peak_tflops": fp32_peak,
+                "fp32_fma_peak_tflops": fp32_peak, "frac_of_fp32_peak": achieved / fp32_peak if fp32_peak else None,
                 "flops_per_move": flops_per_move,
                 "flops_definition": "executed reference-formula operations per trial move counted by the oracle "
                                     "(SURVEY.md §8d unit costs), not the instructions the kernel issues",

@@ -407,6 +407,62 @@ def test_full_size_properties(eng):
     assert len({r.dof[0] for r in res[:2000]}) > 1900
 
 
+@pytest.mark.parametrize("spec,group,n,kw", [
+    (("trimer",), "p2gg", 512, dict(steps=900, inner_steps=300, kt_start=0.1, kt_finish=0.001)),
+    (("lj_circle",), "p1", 512, dict(steps=600, inner_steps=200)),
+    (("polygon", 4), "p2mm", 384, dict(steps=900, inner_steps=300)),
+])
+def test_philox_equivalent_other_configs(eng, spec, group, n, kw):
+    """Same statistical check for the disc molecule with annealing (configs[2]), the LJ circle
+    (configs[3]) and an N = 4 polygon group."""
+    from scipy.stats import ks_2samp
+
+    bopt = orc.build_optimiser(**kw)
+    cstate, ostate = make_states(spec, group)
+    _, res = cp.monte_carlo_best_packing(cstate, c_build(bopt), n, engine=eng, rng=cp.RNG_PHILOX, return_all=True)
+    _, _, ores, _ = orc.analyse_state(ostate, bopt, 0, n, n_threads=os.cpu_count() or 1)
+    a, b = [r.score for r in res], [r.score for r in ores]
+    assert ks_2samp(a, b).pvalue > 1e-3
+
+    def mean_var(v):
+        m = sum(v) / len(v)
+        return m, sum((x - m) ** 2 for x in v) / (len(v) - 1)
+
+    (ma, va), (mb, vb) = mean_var(a), mean_var(b)
+    assert abs(ma - mb) < 4.0 * math.sqrt(va / n + vb / n)  # means agree within 4 standard errors
+    ra, rb = [float(r.rejections) for r in res], [float(r.rejections) for r in ores]
+    (ma, va), (mb, vb) = mean_var(ra), mean_var(rb)
+    assert abs(ma - mb) < 4.0 * math.sqrt(va / n + vb / n)
+
+
+def test_argument_errors(eng):
+    """Error behaviour at the C ABI: bad arguments are refused with a status and a message, never a
+    crash or a silent fallback."""
+    state = cp.PackedState.from_group(cp.LineShape.polygon(5), "p2")
+    sched = cp.BuildOptimiser.cli_defaults(steps=10).pipeline()
+    lib, ctx = eng._lib, eng._ctx
+    arr = (cp.capi.Schedule * 3)(*sched)
+    best = cp.capi.Best()
+    ok = cp.capi.CP_OK
+    assert lib.cp_run(ctx, C.byref(state._problem), arr, 0, 0, 0, 0, 8, None, C.byref(best), None) == cp.capi.CP_ERR_INVALID_ARG
+    assert lib.cp_run(ctx, C.byref(state._problem), arr, 5, 0, 0, 0, 8, None, C.byref(best), None) == cp.capi.CP_ERR_INVALID_ARG
+    assert lib.cp_run(ctx, C.byref(state._problem), arr, 3, 7, 0, 0, 8, None, C.byref(best), None) == cp.capi.CP_ERR_INVALID_ARG
+    assert lib.cp_run(ctx, C.byref(state._problem), arr, 3, 0, 0, 0, 0, None, C.byref(best), None) == cp.capi.CP_ERR_INVALID_ARG
+    assert b"n_replicas" in lib.cp_last_error()
+    bad = cp.capi.Problem()
+    C.memmove(C.byref(bad), C.byref(state._problem), C.sizeof(bad))
+    bad.n_items = 99
+    assert lib.cp_run(ctx, C.byref(bad), arr, 3, 0, 0, 0, 8, None, C.byref(best), None) == cp.capi.CP_ERR_INVALID_ARG
+    assert lib.cp_set_lanes(ctx, 3) == cp.capi.CP_ERR_INVALID_ARG
+    assert lib.cp_launch(C.c_void_p()) == cp.capi.CP_ERR_INVALID_ARG
+    fresh = cp.Engine(0)
+    assert fresh._lib.cp_launch(fresh._ctx) == cp.capi.CP_ERR_NOT_PREPARED
+    fresh.close()
+    assert lib.cp_run(ctx, C.byref(state._problem), arr, 3, 0, 0, 0, 8, None, C.byref(best), None) == ok
+    dc = C.c_int()
+    assert lib.cp_device_count(C.byref(dc)) == ok and dc.value >= 1
+
+
 def test_philox_statistically_equivalent(eng):
     """Free-running production stream vs the oracle's PCG stream: same distribution of final packing
     fractions over replicas (two-sample KS), and the same best packing to 2%."""

@@ -320,7 +320,7 @@ def run_b200(args, rank, local_rank, world):
         if flops_per_move is not None:
             achieved = flops_per_move * moves_per_step_rank / (k_ms * 1e-3) / 1e12
             roofline = {
-                "bound": "fp64", "kernel": ("mc_thread_kernel<POLYGON,%d,PHILOX>" % (args.sides if args.sides in (3, 4, 5, 6) else 0)) if eng.timing().lanes_per_replica == 1 else "mc_kernel<POLYGON,%d,PHILOX>" % eng.timing().lanes_per_replica, "achieved": achieved, "peak": fp64_peak,
+                "bound": "fp64", "kernel": ("mc_thread_kernel<POLYGON,%d,PHILOX>" % (args.sides if 3 <= args.sides <= 12 else 0)) if eng.timing().lanes_per_replica == 1 else "mc_kernel<POLYGON,%d,PHILOX>" % eng.timing().lanes_per_replica, "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                 "traffic": 410368, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
                                                    "(profiles/r1_d_thread_final.txt); algorithmic HBM bytes are the 4.7 MB of results",

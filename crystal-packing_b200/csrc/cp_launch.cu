@@ -17,6 +17,12 @@ size_t cp_thread_shared_bytes(const KProblem &P) { return thread_block_shared_by
         case 4: return cp_thread_polygon_##WHAT##_4(__VA_ARGS__);                                \
         case 5: return cp_thread_polygon_##WHAT##_5(__VA_ARGS__);                                \
         case 6: return cp_thread_polygon_##WHAT##_6(__VA_ARGS__);                                \
+        case 7: return cp_thread_polygon_##WHAT##_7(__VA_ARGS__);                                \
+        case 8: return cp_thread_polygon_##WHAT##_8(__VA_ARGS__);                                \
+        case 9: return cp_thread_polygon_##WHAT##_9(__VA_ARGS__);                                \
+        case 10: return cp_thread_polygon_##WHAT##_10(__VA_ARGS__);                              \
+        case 11: return cp_thread_polygon_##WHAT##_11(__VA_ARGS__);                              \
+        case 12: return cp_thread_polygon_##WHAT##_12(__VA_ARGS__);                              \
         default: return cp_thread_polygon_##WHAT##_0(__VA_ARGS__);                               \
         }                                                                                        \
     case CP_DISCS:                                                                               \

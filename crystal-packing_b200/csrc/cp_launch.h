@@ -40,6 +40,12 @@ CP_DECLARE_THREAD_NI(thread_polygon, 3)
 CP_DECLARE_THREAD_NI(thread_polygon, 4)
 CP_DECLARE_THREAD_NI(thread_polygon, 5)
 CP_DECLARE_THREAD_NI(thread_polygon, 6)
+CP_DECLARE_THREAD_NI(thread_polygon, 7)
+CP_DECLARE_THREAD_NI(thread_polygon, 8)
+CP_DECLARE_THREAD_NI(thread_polygon, 9)
+CP_DECLARE_THREAD_NI(thread_polygon, 10)
+CP_DECLARE_THREAD_NI(thread_polygon, 11)
+CP_DECLARE_THREAD_NI(thread_polygon, 12)
 CP_DECLARE_THREAD_NI(thread_discs, 0)
 CP_DECLARE_THREAD_NI(thread_discs, 1)
 CP_DECLARE_THREAD_NI(thread_discs, 3)

@@ -406,8 +406,13 @@ __device__ __forceinline__ ThreadShared thread_shared(double *smem, int kind, in
 // Monte-Carlo optimisation, one replica per thread (see the header comment for the control flow).
 // Semantics are those of mc_kernel in cp_api.cu: MCOptimiser::optimise_state (optimisation.rs:80-180)
 // for every stage, seeds and bounds per stage as analyse_state / generate_basis set them.
+// Minimum resident blocks per SM, i.e. the register budget: 14 warps per SM hold all 2,048 warps of
+// a 65,536-replica batch at once (<= 146 registers); many-sided polygons are limited by shared
+// memory to fewer warps anyway and get the registers their unrolled n x n tests want.
+constexpr int thread_min_blocks(int ni) { return ni == 0 ? 10 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)); }
+
 template <int KIND, int NI, int RNG>
-__global__ void __launch_bounds__(kThreadBlock, 14) mc_thread_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(NI)) mc_thread_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
     const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);

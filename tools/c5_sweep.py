@@ -19,6 +19,9 @@ for sides in range(3, 13):
         state = cp.PackedState.from_group(cp.LineShape.polygon(sides), g)
         sched = cp.BuildOptimiser.cli_defaults(steps=mc_steps, inner_steps=min(1000, mc_steps)).pipeline()
         moves = n * sum((s.steps // s.inner_steps) * s.inner_steps for s in sched)
+        eng.prepare(state._problem, sched, 64, rng=cp.RNG_PHILOX)  # loads this build of the kernel
+        eng.launch()
+        eng.synchronize()
         eng.prepare(state._problem, sched, n, rng=cp.RNG_PHILOX)
         eng.launch()
         eng.synchronize()

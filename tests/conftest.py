@@ -11,6 +11,13 @@ for p in (_ROOT, os.path.dirname(os.path.abspath(__file__))):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the suites need the two native libraries; build them if this is a fresh checkout
+    lib = os.path.join(_ROOT, "crystal-packing_b200", "lib", "libcpgpu.so")
+    orc = os.path.join(_ROOT, "oracle", "libcp_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import __graft_entry__
+
+        __graft_entry__.build()
 
 
 def _has_gpu():

@@ -36,4 +36,4 @@ from .api import (  # noqa: F401
     load_library,
     monte_carlo_best_packing,
 )
-from . import capi  # noqa: F401
+from . import api, capi  # noqa: F401

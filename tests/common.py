@@ -25,13 +25,33 @@ def make_shapes(spec):
         return cp.LJShape2.from_trimer(r, 120.0, 1.0), orc.trimer(orc.LJ, r)
     if kind == "lj_circle":
         return cp.LJShape2.circle(), orc.circle(orc.LJ)
+    if kind == "discs":  # hand-built molecule: ((x, y, radius), ...) -> the run-time-count kernels
+        atoms = spec[1]
+        shape = cp.MolecularShape2.circle()
+        shape._problem.n_items = len(atoms)
+        for k, a in enumerate(atoms):
+            for c, v in enumerate(a):
+                shape._problem.items[k][c] = v
+        cp.api.refresh_shape(shape)
+        return shape, (orc.DISCS, orc.items_array(atoms))
+    if kind == "lj_sites":  # ((x, y, sigma, epsilon, cutoff), ...)
+        sites = spec[1]
+        shape = cp.LJShape2.circle()
+        shape._problem.n_items = len(sites)
+        for k, a in enumerate(sites):
+            for c, v in enumerate(a):
+                shape._problem.items[k][c] = v
+        cp.api.refresh_shape(shape)
+        return shape, (orc.LJ, orc.items_array(sites))
     raise ValueError(spec)
 
 
 def make_states(spec, group, math_mode=orc.MATH_CP):
     cshape, oshape = make_shapes(spec)
     cls = cp.PotentialState if spec[0].startswith("lj") else cp.PackedState
-    return cls.from_group(cshape, group), orc.state_from_group(oshape, group, math_mode)
+    cstate, ostate = cls.from_group(cshape, group), orc.state_from_group(oshape, group, math_mode)
+    assert cstate.dof == orc.get_dof(ostate)  # same enclosing radius -> same initial cell
+    return cstate, ostate
 
 
 def random_dofs(ostate, n, seed, spread=1.0):

@@ -30,8 +30,15 @@ def eng():
     e.close()
 
 
+DIMER = ("discs", ((-0.6, 0.0, 0.8), (0.6, 0.1, 0.7)))
+TETRAMER = ("discs", ((0.0, 0.0, 1.0), (1.1, 0.0, 0.5), (-1.1, 0.0, 0.5), (0.0, 1.2, 0.4)))
+LJ_DIMER = ("lj_sites", ((-0.5, 0.0, 1.0, 1.0, 3.0), (0.5, 0.0, 0.8, 0.7, 2.5)))
+LJ_PAIR_NOCUT = ("lj_sites", ((-0.4, 0.0, 1.0, 1.0, float("nan")), (0.4, 0.1, 0.9, 1.2, float("nan"))))
+# every build of the kernels: specialised component counts and the run-time-count ones (13-, 16-gons,
+# 2- and 4-disc molecules)
 HARD_SPECS = [("polygon", 3), ("polygon", 4), ("polygon", 5), ("polygon", 8), ("polygon", 12),
-              ("radial", (1.0, 0.6, 1.0, 0.6, 1.0, 0.6)), ("trimer",), ("circle",)]
+              ("polygon", 13), ("polygon", 16), ("radial", (1.0, 0.6, 1.0, 0.6, 1.0, 0.6)), ("trimer",), ("circle",),
+              DIMER, TETRAMER]
 
 
 # ------------------------------------------------------------------ State::score (overlap predicate)
@@ -51,7 +58,7 @@ def test_score_bit_exact_hard(eng, spec, group):
 
 
 @pytest.mark.parametrize("group", GROUPS)
-@pytest.mark.parametrize("spec", [("lj_trimer",), ("lj_trimer", 0.63), ("lj_circle",)])
+@pytest.mark.parametrize("spec", [("lj_trimer",), ("lj_trimer", 0.63), ("lj_circle",), LJ_DIMER, LJ_PAIR_NOCUT])
 def test_score_lj_bit_exact(eng, spec, group):
     cstate, ostate = make_states(spec, group)
     dofs = [orc.get_dof(ostate)] + random_dofs(ostate, 200, seed=17)
@@ -176,6 +183,11 @@ TRAJ_CASES = [
     (("polygon", 5), "p2", dict(steps=6000, inner_steps=200, convergence=1e-3)),
     # steps not a multiple of inner_steps: the remainder is dropped (optimisation.rs:98)
     (("polygon", 4), "p1", dict(steps=1150, inner_steps=300)),
+    # the run-time-count builds of the kernels
+    (("polygon", 13), "p2", dict(steps=600, inner_steps=200)),
+    (("polygon", 16), "p2gg", dict(steps=300, inner_steps=100)),
+    (DIMER, "p2mg", dict(steps=900, inner_steps=300)),
+    (TETRAMER, "p2", dict(steps=900, inner_steps=300)),
 ]
 
 
@@ -265,7 +277,7 @@ def test_lj_trajectories(eng, lanes):
     whole trajectories are bit-identical as well (the contract only asks for 1e-6 relative)."""
     bopt = orc.build_optimiser(steps=600, inner_steps=200)
     for spec, group in ((("lj_trimer",), "p2"), (("lj_circle",), "p1"), (("lj_trimer", 0.63), "p2gg"),
-                        (("lj_circle",), "p2mg")):
+                        (("lj_circle",), "p2mg"), (LJ_DIMER, "p2"), (LJ_PAIR_NOCUT, "p1g1")):
         best, res, idx, obest, ores = run_both(eng, spec, group, bopt, 16, lanes=lanes)
         for k in range(16):
             assert res[k].score == pytest.approx(ores[k].score, rel=LJ_RTOL)

@@ -447,6 +447,50 @@ def test_philox_equivalent_other_configs(eng, spec, group, n, kw):
     assert abs(ma - mb) < 4.0 * math.sqrt(va / n + vb / n)
 
 
+def test_large_replica_ids_and_seed_base(eng):
+    """Seeds are 64-bit: replica ids beyond 2^32 and a seed_base offset reproduce the oracle's
+    seed_from_u64(seed_base + id) streams."""
+    cstate, ostate = make_states(("polygon", 5), "p2")
+    bopt = orc.build_optimiser(steps=300, inner_steps=100)
+    begin = (1 << 40) + 12345
+    best, res = cp.monte_carlo_best_packing(cstate, c_build(bopt), 40, engine=eng, replica_begin=begin, return_all=True)
+    idx, obest, ores, _ = orc.analyse_state(ostate, bopt, begin, 40, n_threads=4)
+    assert [list(r.dof) for r in res] == [list(r.dof) for r in ores]
+    assert best.best_replica == begin + idx
+    # seed_base shifts the seed, not the replica id
+    b2, r2 = eng.run(cstate._problem, c_build(bopt).pipeline(), 40, replica_begin=345, seed_base=(1 << 40) + 12000,
+                     rng=cp.RNG_PCG64MCG)
+    assert [list(r.dof) for r in r2] == [list(r.dof) for r in ores] and b2.replica == 345 + idx
+
+
+def test_external_stream_and_null_outputs(eng):
+    """cp_set_stream with a caller-owned CUDA stream (torch's), and cp_run without out_best."""
+    import torch
+
+    state = cp.PackedState.from_group(cp.LineShape.polygon(4), "p2")
+    sched = cp.BuildOptimiser.cli_defaults(steps=200, inner_steps=100).pipeline()
+    ref_best, ref = eng.run(state._problem, sched, 100, rng=cp.RNG_PHILOX)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    try:
+        eng.prepare(state._problem, sched, 100, rng=cp.RNG_PHILOX)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        eng.launch()
+        stop.record(stream)
+        stream.synchronize()
+        assert start.elapsed_time(stop) > 0
+        out = (cp.capi.ReplicaResult * 100)()
+        best = eng.fetch(out)
+        assert [list(r.dof) for r in out] == [list(r.dof) for r in ref] and best.replica == ref_best.replica
+    finally:
+        eng.set_stream(0)
+    arr = (cp.capi.Schedule * 3)(*sched)
+    out = (cp.capi.ReplicaResult * 100)()
+    assert eng._lib.cp_run(eng._ctx, C.byref(state._problem), arr, 3, cp.RNG_PHILOX, 0, 0, 100, None, None, out) == 0
+    assert [list(r.dof) for r in out] == [list(r.dof) for r in ref]
+
+
 def test_argument_errors(eng):
     """Error behaviour at the C ABI: bad arguments are refused with a status and a message, never a
     crash or a silent fallback."""

@@ -508,3 +508,25 @@ def test_math_modes_agree_closely():
     assert L.orc_exp(orc.MATH_CP, float("-inf")) == 0.0
     assert L.orc_exp(orc.MATH_CP, float("inf")) == math.inf
     assert math.isnan(L.orc_exp(orc.MATH_CP, float("nan")))
+
+
+def test_golden_fixture_matches_oracle():
+    """tests/golden/trajectories.json is what tests/golden/make_golden.py writes today: the oracle
+    in libm mode reproduces every committed final state bit for bit."""
+    import json
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+
+    doc = json.load(open(os.path.join(here, "golden", "trajectories.json")))
+    assert len(doc["cases"]) == len(make_golden.CASES)
+    for case in doc["cases"]:
+        state = orc.state_from_group(make_golden.oracle_shape(case["spec"]), case["group"], orc.MATH_LIBM)
+        bopt = orc.build_optimiser(**case["optimiser"])
+        _, _, results, _ = orc.analyse_state(state, bopt, 0, len(case["replicas"]), n_threads=4)
+        for got, exp in zip(results, case["replicas"]):
+            assert [v.hex() for v in got.dof] == exp["dof"] and got.score.hex() == exp["score"]
+            assert (got.rejections, got.moves) == (exp["rejections"], exp["moves"])

@@ -364,14 +364,38 @@ __device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Do
         const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
         for (int j = 0; j < N; ++j) {
             const double fx0 = g.ld(4 + j * 4 + 0), fy0 = g.ld(4 + j * 4 + 1);
+            if (!(reach < 1e300)) {  // a site without cutoff: every image contributes, nothing to prune
+                for (int ix = -3; ix <= 3; ++ix) {  // periodic_images(position, 3, false): x outer, y inner
+                    const double fx = fx0 + (double)ix;
+                    const double xa = fx * a;
+                    for (int iy = -3; iy <= 3; ++iy) {
+                        if ((ix | iy) == 0) continue;
+                        const double fy = fy0 + (double)iy;  // to_cartesian_translate (cell.rs:241-245)
+                        const double yb = fy * b;
+                        sum += t_shape_energy<NI>(P, g, i, j, xa + yb * t.ca, yb * t.sa);
+                    }
+                }
+                continue;
+            }
+            // the seven image rows of this pair: Y and the skew term depend on iy only, and a row
+            // whose |dy| alone exceeds the reach holds no pair within any cutoff
+            double rowY[7], rowC[7];
+            unsigned rows = 0;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                const double fy = fy0 + (double)(r - 3);  // to_cartesian_translate (cell.rs:241-245)
+                const double yb = fy * b;
+                rowY[r] = yb * t.sa;
+                rowC[r] = yb * t.ca;
+                if (!(fabs(cy - rowY[r]) > reach)) rows |= 1u << r;
+            }
             for (int ix = -3; ix <= 3; ++ix) {  // periodic_images(position, 3, false): x outer, y inner
                 const double fx = fx0 + (double)ix;
                 const double xa = fx * a;
-                for (int iy = -3; iy <= 3; ++iy) {
-                    if ((ix | iy) == 0) continue;
-                    const double fy = fy0 + (double)iy;
-                    const double yb = fy * b;
-                    const double X = xa + yb * t.ca, Y = yb * t.sa;
+#pragma unroll
+                for (int r = 0; r < 7; ++r) {
+                    if (!((rows >> r) & 1u) || (ix == 0 && r == 3)) continue;
+                    const double X = xa + rowC[r], Y = rowY[r];
                     const double ddx = cx - X, ddy = cy - Y;
                     if (ddx * ddx + ddy * ddy > reach_sq) continue;  // every site pair beyond its cutoff
                     sum += t_shape_energy<NI>(P, g, i, j, X, Y);
@@ -409,10 +433,14 @@ __device__ __forceinline__ ThreadShared thread_shared(double *smem, int kind, in
 // Minimum resident blocks per SM, i.e. the register budget: 14 warps per SM hold all 2,048 warps of
 // a 65,536-replica batch at once (<= 146 registers); many-sided polygons are limited by shared
 // memory to fewer warps anyway and get the registers their unrolled n x n tests want.
-constexpr int thread_min_blocks(int ni) { return ni == 0 ? 10 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)); }
+// LJ batches are several waves anyway (configs[3]: 131,072 replicas per GPU) and the row-hoisted
+// image loop wants registers.
+constexpr int thread_min_blocks(int kind, int ni) {
+    return kind == CP_LJ ? 10 : (ni == 0 ? 10 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)));
+}
 
 template <int KIND, int NI, int RNG>
-__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(NI)) mc_thread_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI)) mc_thread_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
     const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);

@@ -328,12 +328,15 @@ __device__ __forceinline__ double t_shape_energy(const KProblem &P, TGeo g, int 
     const int ei = g.comp0 + i * n * 2, ej = g.comp0 + j * n * 2;
     const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
     double e = 0.;
-#pragma unroll
+    // the run-time-count build (NI = 0) keeps these loops rolled: the function is inlined at nine
+    // call sites of t_lj_score and 16 x 16 unrolled pair evaluations each would not compile in
+    // reasonable time
+#pragma unroll(NI > 0 ? NI : 1)
     for (int k = 0; k < (NI > 0 ? NI : CP_MAX_ITEMS); ++k) {
         if (NI == 0 && k >= n) break;
         const double sx = g.ld(ei + k * 2 + 0) + cx, sy = g.ld(ei + k * 2 + 1) + cy;
         const double *it = P.items[k];
-#pragma unroll
+#pragma unroll(NI > 0 ? NI : 1)
         for (int l = 0; l < (NI > 0 ? NI : CP_MAX_ITEMS); ++l) {
             if (NI == 0 && l >= n) break;
             const double ox = g.ld(ej + l * 2 + 0) + X, oy = g.ld(ej + l * 2 + 1) + Y;

@@ -442,8 +442,11 @@ constexpr int thread_min_blocks(int kind, int ni) {
     return kind == CP_LJ ? 10 : (ni == 0 ? 10 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)));
 }
 
-template <int KIND, int NI, int RNG>
-__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI)) mc_thread_kernel(const __grid_constant__ KParams K) {
+// WIDE: the build for problems whose shared-memory footprint caps the occupancy below 12 warps per
+// SM anyway (small polygons in the multiplicity-4 groups): same code, register budget of 8 blocks.
+template <int KIND, int NI, int RNG, bool WIDE = false>
+__global__ void __launch_bounds__(kThreadBlock, WIDE ? 8 : thread_min_blocks(KIND, NI))
+mc_thread_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
     const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);

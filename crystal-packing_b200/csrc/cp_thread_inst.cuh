@@ -7,19 +7,30 @@ static inline size_t thread_shared_bytes(const KProblem &P) {
     return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms);
 }
 
+template <int KIND, int NI, int RNG, bool WIDE>
+static cudaError_t thread_mc_launch(const KParams &K, size_t bytes, cudaStream_t st) {
+    const unsigned grid = (unsigned)((K.n_replicas + kThreadBlock - 1) / kThreadBlock);
+    cudaError_t e = cp_allow_shared(mc_thread_kernel<KIND, NI, RNG, WIDE>, bytes);
+    if (e != cudaSuccess) return e;
+    mc_thread_kernel<KIND, NI, RNG, WIDE><<<grid, kThreadBlock, bytes, st>>>(K);
+    return cudaGetLastError();
+}
+
 template <int KIND, int NI>
 static cudaError_t thread_mc(const KParams &K, cudaStream_t st) {
     const size_t bytes = thread_shared_bytes(K.prob);
-    const unsigned grid = (unsigned)((K.n_replicas + kThreadBlock - 1) / kThreadBlock);
-    cudaError_t e;
+    // hexagons and smaller have a second build with a wider register budget for the cases where
+    // shared memory (not registers) bounds the occupancy: fewer than 12 blocks of this size per SM
+    constexpr bool kHasWide = KIND == CP_POLYGON && NI >= 3 && NI <= 6;
+    const bool wide = kHasWide && bytes * 12 > 227 * 1024;
     if (K.rng_mode == CP_RNG_PCG64MCG) {
-        if ((e = cp_allow_shared(mc_thread_kernel<KIND, NI, CP_RNG_PCG64MCG>, bytes)) != cudaSuccess) return e;
-        mc_thread_kernel<KIND, NI, CP_RNG_PCG64MCG><<<grid, kThreadBlock, bytes, st>>>(K);
-    } else {
-        if ((e = cp_allow_shared(mc_thread_kernel<KIND, NI, CP_RNG_PHILOX>, bytes)) != cudaSuccess) return e;
-        mc_thread_kernel<KIND, NI, CP_RNG_PHILOX><<<grid, kThreadBlock, bytes, st>>>(K);
+        if constexpr (kHasWide)
+            if (wide) return thread_mc_launch<KIND, NI, CP_RNG_PCG64MCG, true>(K, bytes, st);
+        return thread_mc_launch<KIND, NI, CP_RNG_PCG64MCG, false>(K, bytes, st);
     }
-    return cudaGetLastError();
+    if constexpr (kHasWide)
+        if (wide) return thread_mc_launch<KIND, NI, CP_RNG_PHILOX, true>(K, bytes, st);
+    return thread_mc_launch<KIND, NI, CP_RNG_PHILOX, false>(K, bytes, st);
 }
 
 template <int KIND, int NI>

@@ -322,8 +322,8 @@ def run_b200(args, rank, local_rank, world):
             roofline = {
                 "bound": "fp64", "kernel": ("mc_thread_kernel<POLYGON,%d,PHILOX>" % (args.sides if 3 <= args.sides <= 12 else 0)) if eng.timing().lanes_per_replica == 1 else "mc_kernel<POLYGON,%d,PHILOX>" % eng.timing().lanes_per_replica, "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                "traffic": 410368, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                                   "(profiles/r1_d_thread_final.txt); algorithmic HBM bytes are the 4.7 MB of results",
+                "traffic": 1410560, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                                   "(profiles/r1_f_thread_end_of_round.txt); algorithmic HBM bytes are the 4.7 MB of results",
                 "peak_source": "measured here: FP64 FMA chains, 2 flops/FMA (MEASURED_PEAKS.json has no FP64 entry)",
                 "fp32_fma_peak_tflops": fp32_peak, "frac_of_fp32_peak": achieved / fp32_peak if fp32_peak else None,
                 "flops_per_move": flops_per_move,

@@ -447,6 +447,44 @@ def test_philox_equivalent_other_configs(eng, spec, group, n, kw):
     assert abs(ma - mb) < 4.0 * math.sqrt(va / n + vb / n)
 
 
+def test_custom_group_three_operators_hexagonal(eng):
+    """A plane group the reference's table does not hold (three-fold rotation, Hexagonal family:
+    the only cell DOF is the length, cell.rs:136-170, angle fixed at pi/3): three symmetry
+    operators exercise the generic N and the 4-entry basis on both sides."""
+    ops = ["x,y", "-y,x-y", "-x+y,-x"]
+    for spec in (("polygon", 5), ("trimer",)):
+        cshape, oshape = __import__("common").make_shapes(spec)
+        ostate = orc.state_from_group(oshape, "p1", orc.MATH_CP)
+        ostate.family, ostate.n_syms = orc.HEXAGONAL, 3
+        mats = []
+        for i, o in enumerate(ops):
+            assert orc.lib().orc_transform_from_operations(o.encode(), C.byref(ostate.syms[i])) == 0
+            r = ostate.syms[i].rows()
+            mats.append([r[0][0], r[1][0], r[2][0], r[0][1], r[1][1], r[2][1], r[0][2], r[1][2], r[2][2]])
+        radius = orc.lib().orc_shape_enclosing_radius(oshape[0], oshape[1], len(oshape[1]))
+        dof = [4.0 * radius * 3, 1.0, math.pi / 3, -0.5 + 0.5 / 3, -0.5 + 0.5 / 3, 0.0]
+        orc.set_dof(ostate, dof)
+        group = cp.api.group_from_symmetries("p3", "Hexagonal", mats)
+        assert group.key is None
+        cstate = cp.PackedState.from_group(cshape, group)
+        cstate.dof = dof
+        assert len(cstate.generate_basis()) == 4 == orc.lib().orc_state_n_dof(C.byref(ostate))
+        dofs = [dof] + [[dof[0] * f, 1.0, math.pi / 3, x, y, th] for f, x, y, th in
+                        [(0.9, -0.3, -0.2, 0.4), (0.5, 0.1, -0.4, 2.0), (0.3, 0.25, 0.25, 5.0), (0.2, -0.1, 0.3, 1.0)]]
+        ref = oracle_scores(ostate, dofs)
+        for lanes in (1, 8, 32):
+            eng.set_lanes(lanes)
+            got = eng.score(cstate._problem, dofs)
+            assert all(same_float(a, b) for a, b in zip(got, ref)), (spec, lanes, got, ref)
+            sched = cp.MCOptimiser(0.05, 0.5, 0.01, 600, 200, 0, None).schedule
+            _, res = eng.run(cstate._problem, [sched], 12, rng=cp.RNG_PCG64MCG)
+            for k in range(12):
+                s = orc.clone(ostate)
+                rc, _, rej = orc.optimise(s, 0.05, 0.5, 0.01, 600, 200, k)
+                assert rc == 0 and list(res[k].dof) == orc.get_dof(s) and res[k].rejections == rej, (spec, lanes, k)
+        eng.set_lanes(0)
+
+
 def test_large_replica_ids_and_seed_base(eng):
     """Seeds are 64-bit: replica ids beyond 2^32 and a seed_base offset reproduce the oracle's
     seed_from_u64(seed_base + id) streams."""

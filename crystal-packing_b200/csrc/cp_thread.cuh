@@ -478,22 +478,26 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     // different numbers of scored proposals per inner loop (the in-bounds fraction depends on the
     // replica's cell), and synchronising at loop ends would leave the faster lanes idle there.  Only
     // the score phases below are warp-wide.
+    // Per-lane schedule state is kept small (the unrolled test block needs the registers): the
+    // stage's constants are re-read from the kernel parameters at loop ends, and only what every
+    // draw needs lives in registers (the inner-loop length, the step scale, the temperature).
     int stage = 0;
     bool done = !alive;
-    KStage S = K.stages[0];
     double len0 = d.v[0], ratio0 = d.v[1], kt = 0., step_ratio = 1.0, score_start = score_current;
+    double step_scale = 0.;  // max_step_size * step_ratio, the loop-invariant factor of optimisation.rs:115-119
     int convergence_count = 0;
-    unsigned long long outer = 0, loop = 1, it = 0, loop_rejections = 0;
+    unsigned long long inner = 0, loops_left = 0, it = 0, loop_rejections = 0;
     auto begin_stage = [&]() {
-        S = K.stages[stage];
+        const KStage &S = K.stages[stage];
         len0 = d.v[0];  // generate_basis(): bounds captured per optimise_state call (cell.rs:139-152)
         ratio0 = d.v[1];
         rng_begin_stage<RNG>(rng, K.seed_base + replica, replica, n_basis);
         kt = S.kt_start;
         step_ratio = 1.0;
+        step_scale = S.max_step * step_ratio;
         convergence_count = 0;
-        outer = S.inner ? S.steps / S.inner : 0ull;
-        loop = 1;
+        inner = S.inner;
+        loops_left = S.inner ? S.steps / S.inner : 0ull;
         it = 0;
         loop_rejections = 0;
         score_start = score_current;
@@ -506,7 +510,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
                 return;
             }
             begin_stage();
-            if (outer > 0) return;
+            if (loops_left > 0) return;
         }
     };
     if (!done) {
@@ -526,8 +530,9 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
         // and the overlap test is skipped.  Draw order (index, step, threshold) and every
         // decision are unchanged.
         while (!done && !have) {
-            if (it == S.inner) {  // end of an inner loop (optimisation.rs:138-167)
-                moves += S.inner;
+            if (it == inner) {  // end of an inner loop (optimisation.rs:138-167)
+                const KStage &S = K.stages[stage];
+                moves += inner;
                 rejections += loop_rejections;
                 kt *= S.kt_ratio;
                 bool converged = false;
@@ -539,12 +544,13 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
                     }
                 }
                 if (!converged && step_ratio > 1e-4)
-                    step_ratio *= (double)S.inner / ((double)loop_rejections + 1.);
-                ++loop;
+                    step_ratio *= (double)inner / ((double)loop_rejections + 1.);
+                step_scale = S.max_step * step_ratio;
+                --loops_left;
                 it = 0;
                 loop_rejections = 0;
                 score_start = score_current;
-                if (converged || loop > outer) next_stage();
+                if (converged || loops_left == 0) next_stage();
                 continue;
             }
             ++it;
@@ -553,7 +559,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
             rng_draw_move<RNG>(rng, basis_index, sample);
             slot = basis_to_slot(basis_index, n_cell);
             val = d.get(slot);
-            new_val = val + S.max_step * step_ratio * sample;
+            new_val = val + step_scale * sample;
             double lo, hi;
             slot_bounds(slot, len0, ratio0, lo, hi);
             have = lo <= new_val && new_val <= hi;

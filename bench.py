@@ -86,10 +86,13 @@ def cpu_sample(args, seconds, threads):
     bopt = orc.build_optimiser(steps=args.mc_steps, inner_steps=args.inner_steps)
     batch = threads
     total_moves, total_wall, total_flops, done = 0, 0.0, 0.0, 0
+    cpu_sample.best = float("nan")
     while True:
         t0 = time.perf_counter()
-        _, _, res, cnt = orc.analyse_state(state, bopt, done, batch, n_threads=threads, want_counters=True)
+        _, best, res, cnt = orc.analyse_state(state, bopt, done, batch, n_threads=threads, want_counters=True)
         dt = time.perf_counter() - t0
+        if not (cpu_sample.best >= best.score):
+            cpu_sample.best = best.score
         total_wall += dt
         total_moves += sum(r.moves for r in res)
         total_flops += orc.lib().orc_counters_flops(ctypes.byref(cnt))
@@ -121,6 +124,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, world),
+        "best_packing_fraction": cpu_sample.best,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference's rayon path (Rust toolchain absent: "
                                  "the crate cannot be compiled here); gcc -O2 -ffp-contract=off, pthreads"},
@@ -313,7 +317,9 @@ def run_b200(args, rank, local_rank, world):
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{reps} replicas (seeds 0..{reps - 1}) of the same workload, full 3-stage schedule, "
                              f"{w:.1f} s wall",
-                   "note": "C restatement of the reference's rayon path; the Rust crate cannot be built here"}
+                   "best_packing_fraction": cpu_sample.best,
+                   "note": "C restatement of the reference's rayon path; the Rust crate cannot be built here; "
+                           "its best packing is over the sample's replicas only (PCG stream)"}
     roofline = None
     if rank == 0:
         k_ms = sum(kernel_ms) / len(kernel_ms)

@@ -184,6 +184,7 @@ __device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, 
     int count = 0;
     m.incell = 0;
     m.cursor = 0;
+    const double first_row = (double)(-shells);
     for (int i = 0; i < N; ++i) {
         const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
         for (int j = 0; j < N; ++j) {
@@ -193,8 +194,11 @@ __device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, 
                 m.incell |= 1u << (i * N + j);
                 ++count;
             }
-            for (int iy = -shells; iy <= shells; ++iy) {
-                const double fy = fy0 + (double)iy;  // to_cartesian_translate (cell.rs:241-245)
+            // the image offsets as doubles, stepped by 1.0 (exact for these small integers) rather
+            // than converted from the loop counters: int -> double conversions are slow
+            double diy = first_row;
+            for (int iy = -shells; iy <= shells; ++iy, diy += 1.0) {
+                const double fy = fy0 + diy;  // to_cartesian_translate (cell.rs:241-245)
                 const double yb = fy * b;
                 const double ddy = cy - yb * t.sa;
                 if (fabs(ddy) > row_reach) continue;
@@ -204,8 +208,9 @@ __device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, 
                 int lo = __double2int_ru(u - w), hi = __double2int_rd(u + w);
                 lo = lo < -shells ? -shells : lo;
                 hi = hi > shells ? shells : hi;
-                for (int ix = lo; ix <= hi; ++ix) {
-                    const double fx = fx0 + (double)ix;
+                double dix = (double)lo;
+                for (int ix = lo; ix <= hi; ++ix, dix += 1.0) {
+                    const double fx = fx0 + dix;
                     const double ddx = cx - (fx * a + ybca);
                     const bool pass = (ddx * ddx + ddy2) <= radius_sq && (ix | iy) != 0;  // packed.rs:156-157
                     if (pass) bits |= 1ull << ((ix + 3) * 7 + (iy + 3));
@@ -392,8 +397,9 @@ __device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Do
                 rowC[r] = yb * t.ca;
                 if (!(fabs(cy - rowY[r]) > reach)) rows |= 1u << r;
             }
-            for (int ix = -3; ix <= 3; ++ix) {  // periodic_images(position, 3, false): x outer, y inner
-                const double fx = fx0 + (double)ix;
+            double dix = -3.0;
+            for (int ix = -3; ix <= 3; ++ix, dix += 1.0) {  // periodic_images(position, 3, false): x outer, y inner
+                const double fx = fx0 + dix;
                 const double xa = fx * a;
 #pragma unroll
                 for (int r = 0; r < 7; ++r) {

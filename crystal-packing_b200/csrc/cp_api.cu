@@ -148,6 +148,45 @@ static cp_status make_kproblem(const cp_problem *p, KProblem *k) {
         }
         k->lj_reach = cmax + 2. * rmax;
     }
+    // single-precision copies for the certificates (cp_filter.h)
+    for (int s = 0; s < p->n_syms; ++s) {
+        k->symsf[s][0] = (float)p->syms[s][0];
+        k->symsf[s][1] = (float)p->syms[s][1];
+        k->symsf[s][2] = (float)p->syms[s][3];
+        k->symsf[s][3] = (float)p->syms[s][4];
+    }
+    k->radf = (float)p->enclosing_radius;
+    k->chain = 0;
+    if (p->kind == CP_POLYGON) {
+        // a closed chain: every segment ends where the next one starts (LineShape::from_radial computes
+        // the two from different expressions, so they agree to rounding only: line_shape.rs:128-146)
+        bool chain = p->n_items >= 3;
+        const double tol = 1e-12 * p->enclosing_radius;
+        for (int i = 0; i < p->n_items && chain; ++i) {
+            const double *e = p->items[i], *s = p->items[(i + 1) % p->n_items];
+            chain = std::fabs(e[2] - s[0]) <= tol && std::fabs(e[3] - s[1]) <= tol;
+        }
+        k->chain = chain ? 1 : 0;
+        if (cp_thread_route_ni(*k) > 0) {
+            for (int i = 0; i < p->n_items; ++i) {
+                k->ptsf[i][0] = (float)p->items[i][0];
+                k->ptsf[i][1] = (float)p->items[i][1];
+            }
+        } else {
+            for (int i = 0; i < p->n_items; ++i) {
+                k->ptsf[2 * i][0] = (float)p->items[i][0];
+                k->ptsf[2 * i][1] = (float)p->items[i][1];
+                k->ptsf[2 * i + 1][0] = (float)p->items[i][2];
+                k->ptsf[2 * i + 1][1] = (float)p->items[i][3];
+            }
+        }
+    } else if (p->kind == CP_DISCS) {
+        for (int i = 0; i < p->n_items; ++i) {
+            k->ptsf[i][0] = (float)p->items[i][0];
+            k->ptsf[i][1] = (float)p->items[i][1];
+            k->discrf[i] = (float)p->items[i][2];
+        }
+    }
     if (p->kind == CP_LJ)
         for (int i = 0; i < p->n_items; ++i) {
             const double sigma = p->items[i][2], eps = p->items[i][3], x = p->items[i][4];

@@ -1,11 +1,13 @@
 // cp_device.cuh — device code of the Monte-Carlo packing engine (sm_100a).
 //
-// One group of L lanes (L = 4, 8, 16 or 32; a whole warp by default) owns one replica.  The scalar
-// replica state (6 DOFs, score, temperature, step ratio, RNG state) is replicated in the registers
-// of every lane of the group and evolves identically in all of them; the per-move geometry
-// (symmetry images, transformed components) is staged in shared memory by the group; the sweeps
-// over in-cell pairs and periodic-image candidates are strided over the lanes and combined with
-// warp votes (any-overlap, early exit) or shuffle reductions (energy sum).
+// Shared by both kernel families: RNG streams, DOF bookkeeping, the f64 predicates, the Metropolis
+// rule.  The default kernels give every replica one thread (cp_thread.cuh).  The lane-group
+// kernels (cp_group.cuh; on request through cp_set_lanes) give one replica a group of L lanes
+// (L = 4, 8, 16 or 32): the scalar replica state is replicated in the registers of every lane of
+// the group, the per-move geometry is staged in shared memory by the group, and the sweeps over
+// in-cell pairs and periodic-image candidates are strided over the lanes and combined with warp
+// votes (any-overlap, early exit) or shuffle reductions (energy sum); their device functions
+// (build_geometry, hard_overlap, lj_score, state_score) are the second half of this file.
 //
 // Arithmetic contract: every value that feeds a decision is computed with the reference's own
 // expression order in IEEE f64 with no contraction (the file is compiled with -fmad=false), so
@@ -31,6 +33,13 @@ struct KProblem {
     double dof[CP_MAX_DOF];
     double lj_shift[CP_MAX_ITEMS];  // 4*eps*((sigma/x)^12 - (sigma/x)^6) per site (lj2.rs:50-51)
     double lj_reach;  // max cutoff + 2 * max |site position|; +inf when a site has no cutoff
+    // single-precision copies for the certificates of the one-thread-per-replica kernels (cp_filter.h)
+    float symsf[CP_MAX_SYMS][4];        // rotation part of the operators: S[0], S[1], S[3], S[4]
+    float ptsf[2 * CP_MAX_ITEMS][2];    // polygon chain: the n start points; other polygons: start, end
+                                        // of every segment; discs: the centres
+    float discrf[CP_MAX_ITEMS];         // disc radii
+    float radf;                         // enclosing radius
+    int chain;                          // polygon whose segment k ends where segment k + 1 starts
 };
 
 struct KStage {

@@ -2,11 +2,26 @@
 #include "cp_launch.h"
 #include "cp_thread.cuh"
 
-bool cp_thread_kernel_fits(const KProblem &P) {
-    return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms) <= 200 * 1024;
+// component count the one-thread-per-replica build that serves this problem is compiled for
+// (0 = the run-time-count build).  Polygon builds with a compile-time count read the shape as a
+// closed chain of n points and exist for the multiplicities 1, 2 and 4.
+int cp_thread_route_ni(const KProblem &P) {
+    const bool ns_ok = P.n_syms == 1 || P.n_syms == 2 || P.n_syms == 4;
+    switch (P.kind) {
+    case CP_POLYGON: return (P.chain && ns_ok && P.n_items >= 3 && P.n_items <= 12) ? P.n_items : 0;
+    case CP_DISCS: return (ns_ok && (P.n_items == 1 || P.n_items == 3)) ? P.n_items : 0;
+    default: return (P.n_items == 1 || P.n_items == 3) ? P.n_items : 0;
+    }
 }
 
-size_t cp_thread_shared_bytes(const KProblem &P) { return thread_block_shared_bytes(P.kind, P.n_items, P.n_syms); }
+size_t cp_thread_shared_bytes(const KProblem &P) {
+    if (P.kind == CP_LJ) return thread_block_shared_bytes<CP_LJ, 0, 0>(P.n_items, P.n_syms);
+    if (P.kind == CP_POLYGON && cp_thread_route_ni(P) == 0)
+        return thread_block_shared_bytes<CP_POLYGON, 0, 0>(P.n_items, P.n_syms);
+    return thread_block_shared_bytes<CP_DISCS, 0, 0>(P.n_items, P.n_syms);  // one point per component
+}
+
+bool cp_thread_kernel_fits(const KProblem &P) { return cp_thread_shared_bytes(P) <= 200 * 1024; }
 
 // one thread per replica: pick the build specialised for this component count, if there is one
 #define CP_THREAD_ROUTE(WHAT, n_items, ...)                                                      \
@@ -42,18 +57,18 @@ size_t cp_thread_shared_bytes(const KProblem &P) { return thread_block_shared_by
 
 static cudaError_t thread_route_mc(const KParams &K, cudaStream_t st) {
     const int kind = K.prob.kind;
-    CP_THREAD_ROUTE(mc, K.prob.n_items, K, st)
+    CP_THREAD_ROUTE(mc, cp_thread_route_ni(K.prob), K, st)
 }
 static cudaError_t thread_route_score(const KProblem &P, const double *dof, unsigned long long n, double *out,
                                       cudaStream_t st) {
     const int kind = P.kind;
-    CP_THREAD_ROUTE(score, P.n_items, P, dof, n, out, st)
+    CP_THREAD_ROUTE(score, cp_thread_route_ni(P), P, dof, n, out, st)
 }
 static cudaError_t thread_route_replay(const KProblem &P, const double *init, const cp_move *mv,
                                        unsigned long long n_moves, unsigned long long n, cp_decision *out,
                                        cudaStream_t st) {
     const int kind = P.kind;
-    CP_THREAD_ROUTE(replay, P.n_items, P, init, mv, n_moves, n, out, st)
+    CP_THREAD_ROUTE(replay, cp_thread_route_ni(P), P, init, mv, n_moves, n, out, st)
 }
 
 cudaError_t cp_launch_mc(const KParams &K, int lanes, cudaStream_t st) {

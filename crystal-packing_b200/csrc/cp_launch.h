@@ -16,6 +16,9 @@ cudaError_t cp_launch_replay(const KProblem &P, int lanes, const double *init, c
 // does the per-thread geometry of this problem fit the one-thread-per-replica kernels?
 bool cp_thread_kernel_fits(const KProblem &P);
 size_t cp_thread_shared_bytes(const KProblem &P);
+// component count of the build that serves this problem (0 = run-time count); decides how
+// KProblem::ptsf is filled (cp_api.cu)
+int cp_thread_route_ni(const KProblem &P);
 
 // per-kind implementations (cp_group_<kind>.cu, cp_thread_<kind>.cu)
 #define CP_DECLARE_KIND(name)                                                                                  \

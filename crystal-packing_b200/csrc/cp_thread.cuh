@@ -1,462 +1,546 @@
 // cp_thread.cuh — one THREAD per replica (lanes_per_replica = 1), the default kernels.
 //
-// The group kernels (cp_group.cuh) spread one replica over L lanes; profiling them on B200
-// (profiles/r1_a_group32_first.txt) showed ~75 % of the issued instructions were replicated scalar
-// work (RNG, trigonometry, index arithmetic) and votes.  Here every lane owns a whole replica, so
-// all of that is useful work, and the sweeps of one replica run as straight-line loops with the
-// instruction-level parallelism of 25+ independent predicate evaluations.  What SIMT needs in
+// Every lane owns a whole replica: RNG, schedule, DOFs and the Metropolis rule are scalar work that
+// a warp per replica would replicate 32 times (profiles/r1_a_group32_first.txt).  What SIMT needs in
 // return is warp-uniform control flow around the expensive parts, which the move loop provides:
 //   * every lane walks its own (stage, outer loop, inner step) schedule and draws proposals in a
 //     short divergent loop until it holds one that needs scoring: out-of-bounds proposals cost a
 //     draw, and for hard shapes a cell move that the Metropolis rule rejects even if valid is
 //     rejected there too, before any overlap test (the packing fraction depends on the cell only);
-//   * phase A, per lane: geometry into shared memory ([element][thread], conflict-free) and the
-//     exactly pruned sweep over the periodic images; candidates become bits of one 64-bit word per
-//     ordered shape pair;
-//   * phase B, whole warp: the candidates of all 32 replicas are tested in rounds from a shared
-//     pool of 32 entries, one entry per lane, replicas dropping out at their first hit;
+//   * phase A, per lane: positions of the symmetry images in f64 (reference expressions), the
+//     rotated shape points in f32, and the exactly pruned sweep over the periodic images of HALF of
+//     the ordered shape pairs (the reference tests (i, j, t) and its mirror image (j, i, -t); one
+//     certificate covers both, cp_filter.h); candidates become bits of one 64-bit word per pair;
+//   * phase B, whole warp: the candidates of all 32 replicas are drawn in rounds into a shared pool
+//     of 32 entries, one entry per lane.  A lane evaluates the f32 CERTIFICATE of its entry
+//     (cp_filter.h): "every component test is false" / "some component test is true", proven about
+//     the reference's f64 result.  Component pairs it cannot certify go to a warp-wide queue and are
+//     evaluated with the reference's own f64 expressions (both mirror sides, each behind the
+//     reference's own distance filter), one pair per lane.  Replicas drop out at their first hit;
 //   * phase C, per lane: the decision.
-// Arithmetic is the same as cp_device.cuh: reference expression order, f64, no contraction.
+// So every decision is the reference's: certificates only ever replace f64 evaluations whose result
+// they prove.  Arithmetic of everything that reaches a decision: reference expression order, f64,
+// no contraction (-fmad=false).
 #ifndef CP_THREAD_CUH
 #define CP_THREAD_CUH
 
 #include "cp_device.cuh"
+#include "cp_filter.h"
+#include "cp_thread_lj.cuh"
 
 constexpr int kThreadBlock = 32;
+constexpr int kQueueCap = 96;  // component pairs waiting for their f64 evaluation, per warp
 
-// doubles of shared memory each thread needs
-__host__ __device__ inline int thread_geo_doubles(int kind, int n_items, int n_syms) {
-    // per image: fx fy cx cy; per component: the rotated points (polygon: start and end; disc: centre).
-    // Placed coordinates (rotated + position) are re-derived where they are used: two additions
-    // are cheaper than the occupancy a wider per-thread footprint costs.
-    // plus four cell values (a, b, cos, sin of the cell angle) so that ANY lane of the warp can
-    // evaluate a queued candidate of this replica (cooperative drain).
-    return 4 + n_syms * 4 + n_syms * n_items * (kind == CP_POLYGON ? 4 : 2);
+// A shape-pair candidate of one replica: shape i against image (ix, iy) of shape j, |ix|, |iy| <= 3.
+// Bit q = (ix + 3) * 7 + (iy + 3) of the 64-bit word of the pair; the centre bit (ix = iy = 0)
+// stands for the in-cell pair i < j, whose displacement to_cartesian(f_j + (0, 0)) is bit for bit
+// j's own Cartesian position (x + 0.0 == x), so one routine serves both kinds.
+constexpr int kCentreBit = 24;
+// the self images (i == j) come in mirror pairs t, -t: bits with iy > 0, or iy == 0 and ix > 0
+constexpr unsigned long long self_half_mask() {
+    unsigned long long m = 0;
+    for (int ix = -3; ix <= 3; ++ix)
+        for (int iy = -3; iy <= 3; ++iy)
+            if (iy > 0 || (iy == 0 && ix > 0)) m |= 1ull << ((ix + 3) * 7 + (iy + 3));
+    return m;
 }
 
-struct TGeo {
-    double *base;  // element e of this thread is base[e * kThreadBlock]
-    int comp0;     // first component element (= 4 + N * 4); images start at element 4
-    __device__ __forceinline__ double ld(int e) const { return base[e * kThreadBlock]; }
-    __device__ __forceinline__ void st(int e, double v) const { base[e * kThreadBlock] = v; }
+// ---------------------------------------------------------------------------------- shared memory
+// One block = one warp.  Planes are [element][lane] so that a lane's own accesses are conflict-free
+// and any lane can read any replica's column (cooperative tests).
+//   f64 plane : 0 a, 1 b, 2 cos, 3 sin of the cell angle, 4 cos, 5 sin of the site angle, then per
+//               symmetry image s: 6 + 4s + {0 fx, 1 fy (wrapped fractional), 2 cx, 3 cy (Cartesian)}
+//   f32 plane : per image s, per point p: x, y of the rotated point (relative to the image's centre)
+//   masks     : N (N - 1) / 2 pair words + 1 self word (u64)
+//   constants : the shape components and the symmetry operators (f64), for the f64 evaluations
+template <int KIND, int NI, int NS>
+struct TLayout {
+    int n, N, NP;
+    __host__ __device__ TLayout(int n_items, int n_syms)
+        : n(NI > 0 ? NI : n_items), N(NS > 0 ? NS : n_syms), NP((KIND == CP_POLYGON && NI == 0) ? 2 * n : n) {}
+    __host__ __device__ int f64_elems() const { return 6 + 4 * N; }
+    __host__ __device__ int f32_elems() const { return 2 * N * NP; }
+    __host__ __device__ int pairs() const { return N * (N - 1) / 2; }
+    __host__ __device__ int const_doubles() const { return n * 4 + N * 6; }
+    __host__ __device__ size_t bytes() const {
+        return 8 * (size_t)(32 * f64_elems() + 32 * (pairs() + 1) + const_doubles()) + 4 * (size_t)(32 * f32_elems()) +
+               4 * (size_t)(40 + kQueueCap);
+    }
 };
 
-template <int KIND, int NI>
-__device__ __forceinline__ void t_build_geometry(const KProblem &P, TGeo g, const Dof &d, const Trig &t) {
-    const int N = P.n_syms, n = NI > 0 ? NI : P.n_items;
-    constexpr int CW = KIND == CP_POLYGON ? 4 : 2;
+struct TView {
+    double *f64;                // plane base (lane 0)
+    unsigned long long *masks;  // plane base
+    double *c_items, *c_syms;
+    float *f32;       // plane base
+    unsigned *pool;   // [0..31] entries, [32] hit flags
+    unsigned *queue;  // kQueueCap items
+};
+
+template <int KIND, int NI, int NS>
+__device__ __forceinline__ TView thread_view(double *smem, const KProblem &P) {
+    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    TView v;
+    v.f64 = smem;
+    v.masks = reinterpret_cast<unsigned long long *>(smem + 32 * L.f64_elems());
+    v.c_items = smem + 32 * (L.f64_elems() + L.pairs() + 1);
+    v.c_syms = v.c_items + L.n * 4;
+    v.f32 = reinterpret_cast<float *>(v.c_syms + L.N * 6);
+    v.pool = reinterpret_cast<unsigned *>(v.f32 + 32 * L.f32_elems());
+    v.queue = v.pool + 40;
+    return v;
+}
+
+// block constants for the f64 evaluations (any lane, any component index)
+template <int KIND, int NI, int NS>
+__device__ __forceinline__ void thread_stage_constants(const TView &v, const KProblem &P) {
+    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    for (int e = threadIdx.x; e < L.n * 4; e += kThreadBlock) v.c_items[e] = P.items[e >> 2][e & 3];
+    for (int e = threadIdx.x; e < L.N * 6; e += kThreadBlock) v.c_syms[e] = P.syms[e / 6][e % 6];
+    __syncwarp();
+}
+
+// the rotated points of image s of replica `lane` as the certificates read them
+struct TPts {
+    const float *p;  // element 0 of the image, lane column
+    const float *rad;
+    __device__ __forceinline__ float x(int k) const { return p[(2 * k) * 32]; }
+    __device__ __forceinline__ float y(int k) const { return p[(2 * k + 1) * 32]; }
+    __device__ __forceinline__ float r(int k) const { return rad[k]; }
+};
+
+// ---------------------------------------------------------------------------------- phase A
+// OccupiedSite::positions (site.rs:33-45) and Cell2::to_cartesian_isometry (cell.rs:110-112,258-263)
+// in f64 with the reference's expressions; the rotated shape points in f32 for the certificates.
+template <int KIND, int NI, int NS>
+__device__ __forceinline__ void t_place(const KProblem &P, const TView &v, const Dof &d, const Trig &t) {
+    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    double *g = v.f64 + threadIdx.x;
+    float *h = v.f32 + threadIdx.x;
     const double a = d.v[0], b = d.v[0] * d.v[1];
-    g.st(0, a);
-    g.st(1, b);
-    g.st(2, t.ca);
-    g.st(3, t.sa);
-    for (int s = 0; s < N; ++s) {
-        const double *S = P.syms[s];
-        // sym * Transform2::new(theta, (x, y)), rows 0-1 (site.rs:40-45)
-        double m00 = ((S[0] * t.ct) + S[1] * t.st) + S[2] * 0.0;
-        double m01 = ((S[0] * -t.st) + S[1] * t.ct) + S[2] * 0.0;
-        double tx = ((S[0] * d.v[3]) + S[1] * d.v[4]) + S[2] * 1.0;
-        double m10 = ((S[3] * t.ct) + S[4] * t.st) + S[5] * 0.0;
-        double m11 = ((S[3] * -t.st) + S[4] * t.ct) + S[5] * 0.0;
-        double ty = ((S[3] * d.v[3]) + S[4] * d.v[4]) + S[5] * 1.0;
-        double fx = wrap_unit(tx), fy = wrap_unit(ty);
-        double yb = fy * b;
-        g.st(4 + s * 4 + 0, fx);
-        g.st(4 + s * 4 + 1, fy);
-        g.st(4 + s * 4 + 2, fx * a + yb * t.ca);  // cell.rs:258-263
-        g.st(4 + s * 4 + 3, yb * t.sa);
+    g[0 * 32] = a;
+    g[1 * 32] = b;
+    g[2 * 32] = t.ca;
+    g[3 * 32] = t.sa;
+    g[4 * 32] = t.ct;
+    g[5 * 32] = t.st;
+    const float ctf = (float)t.ct, stf = (float)t.st;
 #pragma unroll
-        for (int k = 0; k < (NI > 0 ? NI : CP_MAX_ITEMS); ++k) {
-            if (NI == 0 && k >= n) break;
-            const double *it = P.items[k];
-            const int e = g.comp0 + (s * n + k) * CW;
-            g.st(e + 0, m00 * it[0] + m01 * it[1]);  // Transform * Point without its translation
-            g.st(e + 1, m10 * it[0] + m11 * it[1]);
-            if (KIND == CP_POLYGON) {
-                g.st(e + 2, m00 * it[2] + m01 * it[3]);
-                g.st(e + 3, m10 * it[2] + m11 * it[3]);
+    for (int s = 0; s < (NS > 0 ? NS : CP_MAX_SYMS); ++s) {
+        if (NS == 0 && s >= L.N) break;
+        const double *S = P.syms[s];
+        // translation column of sym * Transform2::new(theta, (x, y)) (site.rs:40-45)
+        const double tx = ((S[0] * d.v[3]) + S[1] * d.v[4]) + S[2] * 1.0;
+        const double ty = ((S[3] * d.v[3]) + S[4] * d.v[4]) + S[5] * 1.0;
+        const double fx = wrap_unit(tx), fy = wrap_unit(ty);
+        const double yb = fy * b;
+        g[(6 + 4 * s + 0) * 32] = fx;
+        g[(6 + 4 * s + 1) * 32] = fy;
+        g[(6 + 4 * s + 2) * 32] = fx * a + yb * t.ca;  // cell.rs:258-263
+        g[(6 + 4 * s + 3) * 32] = yb * t.sa;
+        // rotation block of the same product, single precision (certificates only)
+        const float *F = P.symsf[s];
+        const float m00 = fmaf(F[0], ctf, F[1] * stf), m01 = fmaf(F[1], ctf, -(F[0] * stf));
+        const float m10 = fmaf(F[2], ctf, F[3] * stf), m11 = fmaf(F[3], ctf, -(F[2] * stf));
+        if (NI > 0) {
+#pragma unroll
+            for (int p = 0; p < (NI > 0 ? NI : 1); ++p) {
+                const float px = P.ptsf[p][0], py = P.ptsf[p][1];
+                h[((s * NI + p) * 2 + 0) * 32] = fmaf(m00, px, m01 * py);
+                h[((s * NI + p) * 2 + 1) * 32] = fmaf(m10, px, m11 * py);
+            }
+        } else {
+            for (int p = 0; p < L.NP; ++p) {
+                const float px = P.ptsf[p][0], py = P.ptsf[p][1];
+                h[((s * L.NP + p) * 2 + 0) * 32] = fmaf(m00, px, m01 * py);
+                h[((s * L.NP + p) * 2 + 1) * 32] = fmaf(m10, px, m11 * py);
             }
         }
     }
 }
 
-// shape i in its cell placement against shape j displaced to (X, Y): the image position, or j's own
-// Cartesian position for the in-cell pairs.  Both are shape.transform(&t) = rotated point + t's
-// translation (line_shape.rs:103-108), so one routine serves both.
-template <int KIND, int NI>
-__device__ __forceinline__ bool t_shapes_overlap(const KProblem &P, TGeo g, int i, int j, double X, double Y) {
-    const int n = NI > 0 ? NI : P.n_items;
-    constexpr int CW = KIND == CP_POLYGON ? 4 : 2;
-    bool hit = false;
-    const int ei = g.comp0 + i * n * CW, ej = g.comp0 + j * n * CW;
-    const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
-#pragma unroll
-    for (int l = 0; l < (NI > 0 ? NI : CP_MAX_ITEMS); ++l) {
-        if (NI == 0 && l >= n) break;
-        const int eb = ej + l * CW;
-        const double ox = g.ld(eb + 0) + X, oy = g.ld(eb + 1) + Y;
-        double odx = 0., ody = 0., orad = 0.;
-        if (KIND == CP_POLYGON) {
-            odx = (g.ld(eb + 2) + X) - ox;  // Line2::dx / dy of the placed segment (line2.rs:94-101)
-            ody = (g.ld(eb + 3) + Y) - oy;
-        } else {
-            orad = P.items[l][2];
-        }
-#pragma unroll
-        for (int k = 0; k < (NI > 0 ? NI : CP_MAX_ITEMS); ++k) {
-            if (NI == 0 && k >= n) break;
-            const int ea = ei + k * CW;
-            const double sx = g.ld(ea + 0) + cx, sy = g.ld(ea + 1) + cy;
-            if (KIND == CP_POLYGON) {
-                const double sdx = (g.ld(ea + 2) + cx) - sx, sdy = (g.ld(ea + 3) + cy) - sy;
-                hit |= segments_cross(sx, sy, sdx, sdy, ox, oy, odx, ody);
-            } else {
-                const double rs = P.items[k][2] + orad;  // Atom2::intersects (atom2.rs:21-26)
-                const double dx = sx - ox, dy = sy - oy;
-                hit |= (dx * dx + dy * dy) < rs * rs;
+// candidates of one lane
+struct TCands {
+    unsigned long long cur = 0;  // bits of the current word still to draw
+    int phase = -1;              // words: 0 .. P - 1 the pairs i < j, P .. P + N - 1 the self word once per shape
+    int remaining = 0;
+    unsigned force = 0;          // a candidate sits within rounding of the 2R filter: no certificate is used
+};
+
+// (i << 2) | j of pair word w: pairs in the order (0,1),(0,2),..,(N-2,N-1)
+__device__ __forceinline__ int pair_of_word(int w, int N) {
+    const unsigned lut = N == 4 ? 0xB76321u : (N == 3 ? 0x621u : 0x1u);
+    return (int)((lut >> (4 * w)) & 15u);
+}
+
+// One row-and-column pruned sweep: images (ix, iy) of a shape at fractional (fx0, fy0) against a
+// shape at Cartesian (cx, cy).  A candidate passes the reference's filter when dx*dx + dy*dy <=
+// (2R)^2 (packed.rs:150-157); this sweep keeps everything up to (2R)^2 (1 + 1e-9) and reports whether
+// anything landed within 1e-9 of the threshold (the mirror image's distance differs by rounding).
+// Rows with |dy| beyond the reach and columns outside [(u - 2R)/a, (u + 2R)/a] (widened by 1e-6
+// columns) fail by margins >= 1e6 ulp; what is kept is evaluated with the reference's expressions.
+__device__ __forceinline__ unsigned long long t_sweep_pair(double cx, double cy, double fx0, double fy0, double a,
+                                                           double b, const Trig &t, const CellCache &cc, double r2x,
+                                                           bool self, unsigned &band) {
+    const int shells = cc.shells;
+    const double radius_sq = r2x * r2x;
+    const double wide = radius_sq * (1.0 + 1e-9), narrow = radius_sq * (1.0 - 1e-9);
+    const double row_reach = r2x * (1.0 + 1e-8);
+    const double w = r2x * cc.inv_a * (1.0 + 1e-8) + 1e-6;
+    unsigned long long bits = 0ull;
+    // the image offsets as doubles, stepped by 1.0 (exact for these small integers)
+    double diy = self ? 0.0 : (double)(-shells);
+    for (int iy = self ? 0 : -shells; iy <= shells; ++iy, diy += 1.0) {
+        const double fy = fy0 + diy;  // to_cartesian_translate (cell.rs:241-245)
+        const double yb = fy * b;
+        const double ddy = cy - yb * t.sa;
+        if (fabs(ddy) > row_reach) continue;
+        const double ybca = yb * t.ca, ddy2 = ddy * ddy;
+        const double u = (cx - ybca) * cc.inv_a - fx0;  // column where dx would vanish
+        int lo = __double2int_ru(u - w), hi = __double2int_rd(u + w);
+        lo = lo < -shells ? -shells : lo;
+        hi = hi > shells ? shells : hi;
+        if (self && iy == 0 && lo < 1) lo = 1;
+        double dix = (double)lo;
+        for (int ix = lo; ix <= hi; ++ix, dix += 1.0) {
+            const double fx = fx0 + dix;
+            const double ddx = cx - (fx * a + ybca);
+            const double d2 = ddx * ddx + ddy2;
+            if (d2 <= wide && (ix | iy) != 0) {
+                bits |= 1ull << ((ix + 3) * 7 + (iy + 3));
+                if (!(d2 <= narrow)) band = 1u;
             }
         }
+    }
+    return bits;
+}
+
+// Candidate generation for PackedState::check_intersection (state/packed.rs:127-167), half of the
+// ordered pairs: every in-cell pair i < j (no distance filter there, packed.rs:134-148), every
+// image of j against i for i < j, and the upper half of the self images (taken once, from shape 0:
+// the displacement is the lattice vector whichever the shape).  Returns the candidate count.
+template <int KIND, int NI, int NS>
+__device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const Dof &d, const Trig &t,
+                                        const CellCache &cc, TCands &c) {
+    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    const double *g = v.f64 + threadIdx.x;
+    unsigned long long *m = v.masks + threadIdx.x;
+    const double a = d.v[0], b = d.v[0] * d.v[1];
+    const double r2x = P.radius * 2.;
+    int count = 0, w = 0;
+    unsigned band = 0u;
+#pragma unroll
+    for (int i = 0; i < (NS > 0 ? NS : CP_MAX_SYMS); ++i) {
+        if (NS == 0 && i >= L.N) break;
+        const double cx = g[(6 + 4 * i + 2) * 32], cy = g[(6 + 4 * i + 3) * 32];
+#pragma unroll
+        for (int j = i + 1; j < (NS > 0 ? NS : CP_MAX_SYMS); ++j) {
+            if (NS == 0 && j >= L.N) break;
+            const unsigned long long bits =
+                t_sweep_pair(cx, cy, g[(6 + 4 * j + 0) * 32], g[(6 + 4 * j + 1) * 32], a, b, t, cc, r2x, false, band) |
+                (1ull << kCentreBit);
+            m[w * 32] = bits;
+            ++w;
+            count += __popcll(bits);
+        }
+    }
+    const unsigned long long self =
+        t_sweep_pair(g[(6 + 2) * 32], g[(6 + 3) * 32], g[(6 + 0) * 32], g[(6 + 1) * 32], a, b, t, cc, r2x, true, band);
+    m[w * 32] = self;
+    count += L.N * __popcll(self);
+    c.cur = 0;
+    c.phase = -1;
+    c.remaining = count;
+    c.force = band;
+}
+
+// draws the next candidate of this lane (remaining > 0 guarantees there is one)
+__device__ __forceinline__ void t_pop(TCands &c, const unsigned long long *m, int P, int N, int &ij, int &q) {
+    while (c.cur == 0ull) {
+        ++c.phase;
+        c.cur = m[(c.phase < P ? c.phase : P) * 32];
+    }
+    q = __ffsll((long long)c.cur) - 1;
+    c.cur &= c.cur - 1;
+    ij = c.phase < P ? pair_of_word(c.phase, N) : (c.phase - P) * 5;
+}
+
+// ---------------------------------------------------------------------------------- f64 evaluation
+// One component pair of one candidate with the reference's expressions, both mirror sides:
+//   side A : component k of shape i in its cell placement (self) against component l of image
+//            (ix, iy) of shape j (other)           -- packed.rs:134-148 (in-cell) / :152-165
+//   side A': component l of shape j (self) against component k of image (-ix, -iy) of shape i
+// each behind the reference's own distance filter (packed.rs:156-157; none for the in-cell pair,
+// which has no mirror).  Reads the owner's column of the f64 plane, so any lane can evaluate it.
+// item: owner << 18 | i << 16 | j << 14 | q << 8 | l << 4 | k
+template <int KIND, int NI, int NS>
+__device__ __noinline__ bool t_exact_item(const KProblem &P, const TView &v, unsigned item) {
+    const unsigned owner = item >> 18;
+    const int i = (item >> 16) & 3, j = (item >> 14) & 3, q = (item >> 8) & 63, l = (item >> 4) & 15, k = item & 15;
+    const double *o = v.f64 + owner;
+    const double a = o[0 * 32], b = o[1 * 32], ca = o[2 * 32], sa = o[3 * 32], ct = o[4 * 32], st = o[5 * 32];
+    const double fxi = o[(6 + 4 * i + 0) * 32], fyi = o[(6 + 4 * i + 1) * 32], cxi = o[(6 + 4 * i + 2) * 32],
+                 cyi = o[(6 + 4 * i + 3) * 32];
+    const double fxj = o[(6 + 4 * j + 0) * 32], fyj = o[(6 + 4 * j + 1) * 32], cxj = o[(6 + 4 * j + 2) * 32],
+                 cyj = o[(6 + 4 * j + 3) * 32];
+    const int qx = (q * 37) >> 8;  // q / 7 for q < 49
+    const int ix = qx - 3, iy = q - qx * 7 - 3;
+    const bool incell = q == kCentreBit && i != j;
+    const double r2x = P.radius * 2.;
+    const double radius_sq = r2x * r2x;
+    // rotation blocks of sym * Transform2::new(theta, ..), rows 0-1 (site.rs:40-45)
+    const double *Si = v.c_syms + i * 6, *Sj = v.c_syms + j * 6;
+    const double i00 = ((Si[0] * ct) + Si[1] * st) + Si[2] * 0.0, i01 = ((Si[0] * -st) + Si[1] * ct) + Si[2] * 0.0;
+    const double i10 = ((Si[3] * ct) + Si[4] * st) + Si[5] * 0.0, i11 = ((Si[3] * -st) + Si[4] * ct) + Si[5] * 0.0;
+    const double j00 = ((Sj[0] * ct) + Sj[1] * st) + Sj[2] * 0.0, j01 = ((Sj[0] * -st) + Sj[1] * ct) + Sj[2] * 0.0;
+    const double j10 = ((Sj[3] * ct) + Sj[4] * st) + Sj[5] * 0.0, j11 = ((Sj[3] * -st) + Sj[4] * ct) + Sj[5] * 0.0;
+    const double *ik = v.c_items + k * 4, *jl = v.c_items + l * 4;
+    // Transform * Point without its translation (line_shape.rs:103-108)
+    const double ksx = i00 * ik[0] + i01 * ik[1], ksy = i10 * ik[0] + i11 * ik[1];
+    const double lsx = j00 * jl[0] + j01 * jl[1], lsy = j10 * jl[0] + j11 * jl[1];
+    double kex = 0., key = 0., lex = 0., ley = 0.;
+    if (KIND == CP_POLYGON) {
+        kex = i00 * ik[2] + i01 * ik[3];
+        key = i10 * ik[2] + i11 * ik[3];
+        lex = j00 * jl[2] + j01 * jl[3];
+        ley = j10 * jl[2] + j11 * jl[3];
+    }
+    bool hit = false;
+    {  // side A
+        const double fx = fxj + (double)ix, fy = fyj + (double)iy;  // to_cartesian_translate (cell.rs:241-245)
+        const double yb = fy * b;
+        const double X = fx * a + yb * ca, Y = yb * sa;
+        const double ddx = cxi - X, ddy = cyi - Y;
+        const bool cand = incell || (ddx * ddx + ddy * ddy) <= radius_sq;  // packed.rs:156-157
+        const double sx = ksx + cxi, sy = ksy + cyi, ox = lsx + X, oy = lsy + Y;
+        bool t;
+        if (KIND == CP_POLYGON) {
+            const double sdx = (kex + cxi) - sx, sdy = (key + cyi) - sy;  // Line2::dx / dy (line2.rs:94-101)
+            const double odx = (lex + X) - ox, ody = (ley + Y) - oy;
+            t = segments_cross(sx, sy, sdx, sdy, ox, oy, odx, ody);
+        } else {
+            const double rs = ik[2] + jl[2];  // Atom2::intersects (atom2.rs:21-26)
+            const double dx = sx - ox, dy = sy - oy;
+            t = (dx * dx + dy * dy) < rs * rs;
+        }
+        hit = cand & t;
+    }
+    if (!incell) {  // side A'
+        const double fx = fxi + (double)(-ix), fy = fyi + (double)(-iy);
+        const double yb = fy * b;
+        const double X = fx * a + yb * ca, Y = yb * sa;
+        const double ddx = cxj - X, ddy = cyj - Y;
+        const bool cand = (ddx * ddx + ddy * ddy) <= radius_sq;
+        const double sx = lsx + cxj, sy = lsy + cyj, ox = ksx + X, oy = ksy + Y;
+        bool t;
+        if (KIND == CP_POLYGON) {
+            const double sdx = (lex + cxj) - sx, sdy = (ley + cyj) - sy;
+            const double odx = (kex + X) - ox, ody = (key + Y) - oy;
+            t = segments_cross(sx, sy, sdx, sdy, ox, oy, odx, ody);
+        } else {
+            const double rs = jl[2] + ik[2];
+            const double dx = sx - ox, dy = sy - oy;
+            t = (dx * dx + dy * dy) < rs * rs;
+        }
+        hit |= cand & t;
     }
     return hit;
 }
 
-// A shape-pair candidate of one replica: shape i against image (ix, iy) of shape j, |ix|, |iy| <= 3.
-// Bit q = (ix + 3) * 7 + (iy + 3) of the 64-bit word of the ordered pair (i, j); the centre bit
-// (ix = iy = 0) stands for the in-cell pair i < j, whose displacement to_cartesian(f_j + (0, 0)) is
-// bit for bit j's own Cartesian position (x + 0.0 == x), so one routine tests both kinds.
-constexpr int kCentreBit = 24;
-
-// shape.transform(&transform2) + intersects for candidate bit q of pair word `ij` of the replica
-// whose geometry is `g` (packed.rs:134-148,158-161).  Reads only shared memory, so any lane of the
-// warp can evaluate it.
-template <int KIND, int NI>
-__device__ __forceinline__ bool t_test_candidate(const KProblem &P, TGeo g, int i, int j, int q) {
-    const int qx = (q * 37) >> 8;  // q / 7 for q < 49
-    const int ix = qx - 3, iy = q - qx * 7 - 3;
-    const double a = g.ld(0), b = g.ld(1), ca = g.ld(2), sa = g.ld(3);
-    const double fx = g.ld(4 + j * 4 + 0) + (double)ix;  // to_cartesian_translate (cell.rs:241-245)
-    const double fy = g.ld(4 + j * 4 + 1) + (double)iy;
-    const double yb = fy * b;
-    return t_shapes_overlap<KIND, NI>(P, g, i, j, fx * a + yb * ca, yb * sa);
-}
-
-// Candidate masks of one thread: N*N image words in shared memory, [word][thread]; the in-cell
-// pairs (which word's centre bit is meant) and the scan cursor stay in registers.
-struct CandMasks {
-    unsigned long long *base;
-    unsigned incell = 0;  // bit w set: in-cell pair of word w still to test
-    int cursor = 0;       // words below it are exhausted
-    __device__ __forceinline__ unsigned long long ld(int w) const { return base[w * kThreadBlock]; }
-    __device__ __forceinline__ void st(int w, unsigned long long v) const { base[w * kThreadBlock] = v; }
-};
-
-// per-replica values that depend on the cell DOFs only, kept across moves
-struct CellCache {
-    int shells;    // periodic_range (packed.rs:128-132)
-    double inv_a;  // 1 / a, used only to bound the image columns worth testing (never in a decision)
-};
-__device__ __forceinline__ CellCache cell_cache_of(const Dof &d) {
-    CellCache c;
-    c.shells = periodic_range(d.v[0], d.v[0] * d.v[1], d.v[2]);
-    c.inv_a = 1.0 / d.v[0];
-    return c;
-}
-
-// PackedState::check_intersection (state/packed.rs:127-167), candidate generation: every in-cell
-// pair i < j (no distance filter there, packed.rs:134-148) and every periodic image that passes
-// the 2R distance filter (packed.rs:150-157) is recorded as a bit; the caller tests them
-// (t_drain_local, or the warp-cooperative drain of the MC kernel).  Returns the number of bits set.
-template <int KIND, int NI>
-__device__ __forceinline__ int t_sweep(const KProblem &P, TGeo g, const Dof &d, const Trig &t, const CellCache &cc,
-                                       CandMasks &m) {
-    const int N = P.n_syms, shells = cc.shells;
-    const double a = d.v[0], b = d.v[0] * d.v[1];
-    const double r2x = P.radius * 2.;
-    const double radius_sq = r2x * r2x;
-    // Exact pruning of the (2*shells+1)^2 image sweep.  A candidate passes only if dx*dx + dy*dy <=
-    // (2R)^2, so (a) a row (fixed iy) with |dy| > 2R(1 + 1e-12) cannot pass, and (b) within a row
-    // only the columns with |dx| <= 2R can: ix in [(u - 2R)/a, (u + 2R)/a] with u the row's offset.
-    // The column bounds are computed approximately and widened by 1e-6 columns (a distance of
-    // 1e-6 * a, against rounding errors of ~1e-15), so every candidate left out fails the
-    // reference's filter by a wide margin; the ones kept are evaluated with the reference's
-    // expressions, bit for bit.
-    const double row_reach = r2x * (1.0 + 1e-12);
-    int count = 0;
-    m.incell = 0;
-    m.cursor = 0;
-    const double first_row = (double)(-shells);
-    for (int i = 0; i < N; ++i) {
-        const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
-        for (int j = 0; j < N; ++j) {
-            const double fx0 = g.ld(4 + j * 4 + 0), fy0 = g.ld(4 + j * 4 + 1);
-            unsigned long long bits = 0ull;
-            if (j > i) {
-                m.incell |= 1u << (i * N + j);
-                ++count;
-            }
-            // the image offsets as doubles, stepped by 1.0 (exact for these small integers) rather
-            // than converted from the loop counters: int -> double conversions are slow
-            double diy = first_row;
-            for (int iy = -shells; iy <= shells; ++iy, diy += 1.0) {
-                const double fy = fy0 + diy;  // to_cartesian_translate (cell.rs:241-245)
-                const double yb = fy * b;
-                const double ddy = cy - yb * t.sa;
-                if (fabs(ddy) > row_reach) continue;
-                const double ybca = yb * t.ca, ddy2 = ddy * ddy;
-                const double u = (cx - ybca) * cc.inv_a - fx0;  // column where dx would vanish
-                const double w = r2x * cc.inv_a + 1e-6;
-                int lo = __double2int_ru(u - w), hi = __double2int_rd(u + w);
-                lo = lo < -shells ? -shells : lo;
-                hi = hi > shells ? shells : hi;
-                double dix = (double)lo;
-                for (int ix = lo; ix <= hi; ++ix, dix += 1.0) {
-                    const double fx = fx0 + dix;
-                    const double ddx = cx - (fx * a + ybca);
-                    const bool pass = (ddx * ddx + ddy2) <= radius_sq && (ix | iy) != 0;  // packed.rs:156-157
-                    if (pass) bits |= 1ull << ((ix + 3) * 7 + (iy + 3));
-                }
-            }
-            m.st(i * N + j, bits);
-            count += __popcll(bits);
+// evaluates the queued component pairs, one per lane; owners that already have a hit are skipped
+template <int KIND, int NI, int NS>
+__device__ __forceinline__ void t_flush(const KProblem &P, const TView &v, int qcount) {
+    const unsigned lane = threadIdx.x & 31u;
+    __syncwarp();
+    for (int base = 0; base < qcount; base += 32) {
+        const int idx = base + (int)lane;
+        if (idx < qcount) {
+            const unsigned item = v.queue[idx];
+            const unsigned owner = item >> 18;
+            if (!((*(volatile unsigned *)&v.pool[32] >> owner) & 1u))
+                if (t_exact_item<KIND, NI, NS>(P, v, item)) atomicOr(&v.pool[32], 1u << owner);
         }
     }
-    return count;
+    __syncwarp();
 }
 
-// pops the next candidate of this thread: in-cell pairs first (they decide most moves), then the
-// image candidates in pair / bit order.  Returns false when none is left.
-__device__ __forceinline__ bool t_pop_candidate(CandMasks &m, int NN, int &ij, int &q) {
-    if (m.incell) {
-        ij = __ffs((int)m.incell) - 1;
-        m.incell &= m.incell - 1;
-        q = kCentreBit;
-        return true;
-    }
-    while (m.cursor < NN) {
-        const unsigned long long bits = m.ld(m.cursor);
-        if (bits) {
-            q = __ffsll((long long)bits) - 1;
-            m.st(m.cursor, bits & (bits - 1));
-            ij = m.cursor;
-            return true;
-        }
-        ++m.cursor;
-    }
-    return false;
-}
-
-template <int KIND, int NI>
-__device__ __forceinline__ bool t_drain_local(const KProblem &P, TGeo g, CandMasks &m) {
-    const int N = P.n_syms, NN = N * N;
-    int ij, q;
-    while (t_pop_candidate(m, NN, ij, q)) {
-        const int i = ij / N;
-        if (t_test_candidate<KIND, NI>(P, g, i, ij - i * N, q)) return true;
-    }
-    return false;
-}
-
-// Warp-cooperative drain.  The number of candidates varies a lot between replicas (1 .. dozens in
-// dense, elongated cells), and a lane-local loop would make every lane wait for the longest list
-// while most replicas are decided by their first hit.  So the warp works in rounds: every replica
-// that is still undecided contributes its next few candidates to a pool of at most 32, the lanes
-// test one pool entry each (reading the owner's geometry from shared memory), owners with a hit
-// drop out.  `remaining` = this lane's candidate count (0 for lanes without a proposal).  Must be
-// called by all 32 lanes converged; pool = 33 words of shared memory per warp.
-template <int KIND, int NI>
-__device__ __forceinline__ bool t_drain_warp(const KProblem &P, double *smem_geo, unsigned *pool, CandMasks &m,
-                                             int remaining) {
-    const unsigned lane = threadIdx.x & 31u, warp_first = threadIdx.x & ~31u;
-    const int N = P.n_syms, NN = N * N, comp0 = 4 + N * 4;
-    bool hit = false;
+// ---------------------------------------------------------------------------------- phase B
+// PackedState::check_intersection for the 32 replicas of the warp at once (see the header comment).
+// Must be called by all 32 lanes converged; lanes without a proposal pass remaining = 0.
+template <int KIND, int NI, int NS>
+__device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v, TCands &c) {
+    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    constexpr int W = NI > 0 ? cpf_words(NI) : CPF_MAX_WORDS;
+    const unsigned lane = threadIdx.x & 31u;
+    const int NP2 = L.NP * 2, PW = L.pairs(), nn = L.n * L.n;
+    const unsigned long long *my_masks = v.masks + lane;
+    int qcount = 0;  // warp-uniform
+    if (lane == 0) v.pool[32] = 0u;
+    __syncwarp();
     for (;;) {
-        const unsigned wanting = __ballot_sync(0xffffffffu, remaining > 0);
+        const unsigned wanting = __ballot_sync(0xffffffffu, c.remaining > 0);
         if (wanting == 0u) break;
-        const int quota = 32 / __popc(wanting);  // >= 1; pool never exceeds 32 entries
-        const int take = remaining < quota ? remaining : quota;
+        const int quota = 32 / __popc(wanting);  // >= 1; the pool never exceeds 32 entries
+        const int take = c.remaining < quota ? c.remaining : quota;
         int incl = take;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += v;
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         int slot = incl - take;
         for (int k = 0; k < take; ++k) {
             int ij, q;
-            t_pop_candidate(m, NN, ij, q);
-            const int i = N == 1 ? 0 : (N == 2 ? ij >> 1 : (N == 4 ? ij >> 2 : (ij * 11) >> 5));  // ij / N, N <= 4
-            pool[slot++] = (lane << 10) | (unsigned)(i << 8) | (unsigned)((ij - i * N) << 6) | (unsigned)q;
+            t_pop(c, my_masks, PW, L.N, ij, q);
+            v.pool[slot++] = (lane << 11) | (c.force << 10) | (unsigned)(ij << 6) | (unsigned)q;
         }
-        remaining -= take;
-        if (lane == 0) pool[32] = 0u;
+        c.remaining -= take;
         __syncwarp();
+        // one entry per lane: the certificate
+        unsigned amb[W];
+        int count = 0;
+        unsigned entry = 0u;
         if ((int)lane < total) {
-            const unsigned entry = pool[lane];
-            const unsigned owner = entry >> 10;
-            const TGeo og{smem_geo + warp_first + owner, comp0};
-            if (t_test_candidate<KIND, NI>(P, og, (int)((entry >> 8) & 3u), (int)((entry >> 6) & 3u),
-                                           (int)(entry & 63u)))
-                atomicOr(&pool[32], 1u << owner);
+            entry = v.pool[lane];
+            const unsigned owner = entry >> 11, force = (entry >> 10) & 1u;
+            const int i = (entry >> 8) & 3, j = (entry >> 6) & 3, q = entry & 63;
+            const double *o = v.f64 + owner;
+            const int qx = (q * 37) >> 8;  // q / 7 for q < 49
+            const int ix = qx - 3, iy = q - qx * 7 - 3;
+            // image position of shape j relative to shape i: to_cartesian_translate (cell.rs:241-245)
+            const double a = o[0 * 32], b = o[1 * 32], ca = o[2 * 32], sa = o[3 * 32];
+            const double fx = o[(6 + 4 * j + 0) * 32] + (double)ix, fy = o[(6 + 4 * j + 1) * 32] + (double)iy;
+            const double yb = fy * b;
+            const float dX = (float)((fx * a + yb * ca) - o[(6 + 4 * i + 2) * 32]);
+            const float dY = (float)(yb * sa - o[(6 + 4 * i + 3) * 32]);
+            const TPts A{v.f32 + owner + (i * NP2) * 32, P.discrf}, B{v.f32 + owner + (j * NP2) * 32, P.discrf};
+            float cmin, tau;
+            if constexpr (KIND == CP_POLYGON) {
+                tau = cpf_tau(P.radf, dX, dY);
+                if constexpr (NI > 0)
+                    cmin = cpf_chain<NI>(A, B, dX, dY, tau, amb);
+                else
+                    cmin = cpf_segments(L.n, A, B, dX, dY, tau, amb);
+            } else {
+                tau = cpf_tau_discs(P.radf, dX, dY);
+                cmin = cpf_discs<NI>(L.n, A, B, dX, dY, tau, amb);
+            }
+            if (force) {  // candidacy itself is in doubt: every component pair goes through the f64 path
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const int left = nn - 32 * w;
+                    amb[w] = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+                }
+                count = nn;
+            } else if (cmin < -tau) {
+                atomicOr(&v.pool[32], 1u << owner);  // certified: some component test is true
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; ++w) count += __popc(amb[w]);
+            }
         }
-        __syncwarp();
-        if ((pool[32] >> lane) & 1u) {
-            hit = true;
-            remaining = 0;  // decided: the rest of this replica's candidates need no test
-        }
-        __syncwarp();  // pool is rewritten by the next round
-    }
-    return hit;
-}
-
-template <int NI>
-__device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Dof &d, const Trig &t,
-                                             const CellCache &cc);
-
-// State::score for one replica in one thread, everything local (batch score, replay, initial score)
-template <int KIND, int NI>
-__device__ __forceinline__ double t_state_score(const KProblem &P, TGeo g, CandMasks m, const Dof &d,
-                                                const Trig &t) {
-    if constexpr (KIND == CP_LJ) return t_lj_score<NI>(P, g, d, t, cell_cache_of(d));
-    t_build_geometry<KIND, NI>(P, g, d, t);
-    t_sweep<KIND, NI>(P, g, d, t, cell_cache_of(d), m);
-    const bool overlap = t_drain_local<KIND, NI>(P, g, m);
-    const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
-    return overlap ? __longlong_as_double(0x7FF8000000000000ll) : (P.area * (double)P.n_syms) / cell_area;
-}
-
-// LJShape2::energy (shape/lj_shape.rs:35-39): iproduct!(self.items, other.items) summed in order,
-// `other` = shape j displaced to (X, Y)
-template <int NI>
-__device__ __forceinline__ double t_shape_energy(const KProblem &P, TGeo g, int i, int j, double X, double Y) {
-    const int n = NI > 0 ? NI : P.n_items;
-    const int ei = g.comp0 + i * n * 2, ej = g.comp0 + j * n * 2;
-    const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
-    double e = 0.;
-    // the run-time-count build (NI = 0) keeps these loops rolled: the function is inlined at nine
-    // call sites of t_lj_score and 16 x 16 unrolled pair evaluations each would not compile in
-    // reasonable time
-#pragma unroll(NI > 0 ? NI : 1)
-    for (int k = 0; k < (NI > 0 ? NI : CP_MAX_ITEMS); ++k) {
-        if (NI == 0 && k >= n) break;
-        const double sx = g.ld(ei + k * 2 + 0) + cx, sy = g.ld(ei + k * 2 + 1) + cy;
-        const double *it = P.items[k];
-#pragma unroll(NI > 0 ? NI : 1)
-        for (int l = 0; l < (NI > 0 ? NI : CP_MAX_ITEMS); ++l) {
-            if (NI == 0 && l >= n) break;
-            const double ox = g.ld(ej + l * 2 + 0) + X, oy = g.ld(ej + l * 2 + 1) + Y;
-            e += lj_pair(sx - ox, sy - oy, it[2], it[3], it[4], P.lj_shift[k]);
-        }
-    }
-    return e;
-}
-
-// PotentialState::score (state/potential.rs:82-115) for one replica in one thread: the reference's
-// accumulation order is simply the loop order here.  Exact pruning: when every site has a cutoff,
-// a shape pair whose centres are further apart than max cutoff + 2 max|site| (P.lj_reach, widened
-// by 1e-9) has all its site distances beyond the cutoff, each LJ2::energy is exactly 0.0 and adding
-// it cannot change the sum - so the pair, its row or its columns are skipped outright.
-template <int NI>
-__device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Dof &d, const Trig &t,
-                                             const CellCache &cc) {
-    t_build_geometry<CP_LJ, NI>(P, g, d, t);
-    const int N = P.n_syms;
-    const double a = d.v[0], b = d.v[0] * d.v[1];
-    const double reach = P.lj_reach * (1.0 + 1e-9);  // +inf: no pruning
-    const double reach_sq = reach * reach;
-    double sum = 0.;
-    for (int i = 0; i < N; ++i)
-        for (int j = i + 1; j < N; ++j)
-            sum += t_shape_energy<NI>(P, g, i, j, g.ld(4 + j * 4 + 2), g.ld(4 + j * 4 + 3));
-    for (int i = 0; i < N; ++i) {
-        const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
-        for (int j = 0; j < N; ++j) {
-            const double fx0 = g.ld(4 + j * 4 + 0), fy0 = g.ld(4 + j * 4 + 1);
-            if (!(reach < 1e300)) {  // a site without cutoff: every image contributes, nothing to prune
-                for (int ix = -3; ix <= 3; ++ix) {  // periodic_images(position, 3, false): x outer, y inner
-                    const double fx = fx0 + (double)ix;
-                    const double xa = fx * a;
-                    for (int iy = -3; iy <= 3; ++iy) {
-                        if ((ix | iy) == 0) continue;
-                        const double fy = fy0 + (double)iy;  // to_cartesian_translate (cell.rs:241-245)
-                        const double yb = fy * b;
-                        sum += t_shape_energy<NI>(P, g, i, j, xa + yb * t.ca, yb * t.sa);
+        // component pairs without a certificate: queue them for the f64 evaluation
+        const int fresh = __reduce_add_sync(0xffffffffu, count);
+        if (fresh > 0) {
+            if (qcount + fresh > kQueueCap) {
+                t_flush<KIND, NI, NS>(P, v, qcount);
+                qcount = 0;
+            }
+            const unsigned head = (entry >> 11) << 18 | ((entry >> 6) & 15u) << 14 | (entry & 63u) << 8;
+            if (fresh > kQueueCap) {
+                // degenerate amounts (aligned mirror images at theta = 0): each lane evaluates its own
+                bool h = false;
+                if (count > 0) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        unsigned bits = amb[w];
+                        while (bits && !h) {
+                            const int p = 32 * w + __ffs((int)bits) - 1;
+                            bits &= bits - 1;
+                            const int l = p / L.n, k = p - l * L.n;
+                            h = t_exact_item<KIND, NI, NS>(P, v, head | (unsigned)(l << 4) | (unsigned)k);
+                        }
+                    }
+                    if (h) atomicOr(&v.pool[32], 1u << (entry >> 11));
+                }
+            } else {
+                int inc2 = count;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if ((int)lane >= o) inc2 += up;
+                }
+                int at = qcount + inc2 - count;
+                if (count > 0) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        unsigned bits = amb[w];
+                        while (bits) {
+                            const int p = 32 * w + __ffs((int)bits) - 1;
+                            bits &= bits - 1;
+                            const int l = p / L.n, k = p - l * L.n;
+                            v.queue[at++] = head | (unsigned)(l << 4) | (unsigned)k;
+                        }
                     }
                 }
-                continue;
-            }
-            // the seven image rows of this pair: Y and the skew term depend on iy only, and a row
-            // whose |dy| alone exceeds the reach holds no pair within any cutoff
-            double rowY[7], rowC[7];
-            unsigned rows = 0;
-#pragma unroll
-            for (int r = 0; r < 7; ++r) {
-                const double fy = fy0 + (double)(r - 3);  // to_cartesian_translate (cell.rs:241-245)
-                const double yb = fy * b;
-                rowY[r] = yb * t.sa;
-                rowC[r] = yb * t.ca;
-                if (!(fabs(cy - rowY[r]) > reach)) rows |= 1u << r;
-            }
-            double dix = -3.0;
-            for (int ix = -3; ix <= 3; ++ix, dix += 1.0) {  // periodic_images(position, 3, false): x outer, y inner
-                const double fx = fx0 + dix;
-                const double xa = fx * a;
-#pragma unroll
-                for (int r = 0; r < 7; ++r) {
-                    if (!((rows >> r) & 1u) || (ix == 0 && r == 3)) continue;
-                    const double X = xa + rowC[r], Y = rowY[r];
-                    const double ddx = cx - X, ddy = cy - Y;
-                    if (ddx * ddx + ddy * ddy > reach_sq) continue;  // every site pair beyond its cutoff
-                    sum += t_shape_energy<NI>(P, g, i, j, X, Y);
-                }
+                qcount += fresh;
             }
         }
+        __syncwarp();
+        if ((v.pool[32] >> lane) & 1u) c.remaining = 0;  // decided: the rest of this replica's candidates need no test
+        __syncwarp();                                    // the pool is rewritten by the next round
     }
-    return -sum / (double)N;
+    if (qcount > 0) t_flush<KIND, NI, NS>(P, v, qcount);
+    return (v.pool[32] >> lane) & 1u;
 }
 
-// shared memory of a block: per-thread geometry, per-thread candidate masks, one pool per warp
-__host__ __device__ inline size_t thread_block_shared_bytes(int kind, int n_items, int n_syms) {
-    return sizeof(double) * kThreadBlock * (size_t)(thread_geo_doubles(kind, n_items, n_syms) + n_syms * n_syms) +
-           sizeof(unsigned) * 40 * (kThreadBlock / 32);
-}
-struct ThreadShared {
-    TGeo g;
-    CandMasks m;
-    unsigned long long *masks_all;
-    unsigned *pool;
-};
-__device__ __forceinline__ ThreadShared thread_shared(double *smem, int kind, int n_items, int n_syms) {
-    ThreadShared s;
-    const int geo = thread_geo_doubles(kind, n_items, n_syms);
-    s.g = TGeo{smem + threadIdx.x, 4 + n_syms * 4};
-    s.masks_all = reinterpret_cast<unsigned long long *>(smem + kThreadBlock * geo);
-    s.m.base = s.masks_all + threadIdx.x;
-    s.pool = reinterpret_cast<unsigned *>(smem + kThreadBlock * (geo + n_syms * n_syms)) + (threadIdx.x >> 5) * 40;
-    return s;
+// State::score for the warp's 32 replicas (batch score, replay, initial score); warp-collective.
+// LJ: everything is lane-local.
+template <int KIND, int NI, int NS>
+__device__ __forceinline__ double t_state_score(const KProblem &P, const TView &v, double *smem, const Dof &d,
+                                                const Trig &t, bool live) {
+    if constexpr (KIND == CP_LJ) {
+        const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
+        return t_lj_score<NI>(P, g, d, t, cell_cache_of(d));
+    } else {
+        TCands c;
+        if (live) {
+            t_place<KIND, NI, NS>(P, v, d, t);
+            t_sweep<KIND, NI, NS>(P, v, d, t, cell_cache_of(d), c);
+        }
+        const bool overlap = t_overlap_warp<KIND, NI, NS>(P, v, c);
+        const double cell_area = t.sa * d.v[0] * (d.v[0] * d.v[1]);
+        return overlap ? __longlong_as_double(0x7FF8000000000000ll) : (P.area * (double)P.n_syms) / cell_area;
+    }
 }
 
-// Monte-Carlo optimisation, one replica per thread (see the header comment for the control flow).
-// Semantics are those of mc_kernel in cp_api.cu: MCOptimiser::optimise_state (optimisation.rs:80-180)
-// for every stage, seeds and bounds per stage as analyse_state / generate_basis set them.
-// Minimum resident blocks per SM, i.e. the register budget: 14 warps per SM hold all 2,048 warps of
-// a 65,536-replica batch at once (<= 146 registers); many-sided polygons are limited by shared
-// memory to fewer warps anyway and get the registers their unrolled n x n tests want.
-// LJ batches are several waves anyway (configs[3]: 131,072 replicas per GPU) and the row-hoisted
-// image loop wants registers.
+// shared memory of a block
+template <int KIND, int NI, int NS>
+__host__ __device__ inline size_t thread_block_shared_bytes(int n_items, int n_syms) {
+    if (KIND == CP_LJ) return sizeof(double) * kThreadBlock * (size_t)lj_geo_doubles(n_items, n_syms);
+    return TLayout<KIND, NI, NS>(n_items, n_syms).bytes();
+}
+
+// Monte-Carlo optimisation, one replica per thread (see the header comment for the control flow):
+// MCOptimiser::optimise_state (optimisation.rs:80-180) for every stage, seeds and bounds per stage
+// as analyse_state / generate_basis set them.
+// Register budget = minimum resident blocks per SM: 14 warps per SM hold all 2,048 warps of a
+// 65,536-replica batch at once (<= 146 registers).
 constexpr int thread_min_blocks(int kind, int ni) {
-    return kind == CP_LJ ? 10 : (ni == 0 ? 10 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)));
+    return kind == CP_LJ ? 10 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)));
 }
 
-// WIDE: the build for problems whose shared-memory footprint caps the occupancy below 12 warps per
-// SM anyway (small polygons in the multiplicity-4 groups): same code, register budget of 8 blocks.
-template <int KIND, int NI, int RNG, bool WIDE = false>
-__global__ void __launch_bounds__(kThreadBlock, WIDE ? 8 : thread_min_blocks(KIND, NI))
+template <int KIND, int NI, int NS, int RNG>
+__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI))
 mc_thread_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
-    const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);
-    const TGeo g = sh.g;
+    TView v{};
+    if constexpr (KIND != CP_LJ) {
+        v = thread_view<KIND, NI, NS>(smem, P);
+        thread_stage_constants<KIND, NI, NS>(v, P);
+    }
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
     const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
     const unsigned long long replica = K.replica_begin + (active ? rep : 0ull);
@@ -472,21 +556,17 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     const int n_cell = n_cell_dof(P.family);
     const int n_basis = n_cell + 3;
     unsigned long long rejections = 0, moves = 0;
-    double score_current = t_state_score<KIND, NI>(P, g, sh.m, d, t);
+    double score_current = t_state_score<KIND, NI, NS>(P, v, smem, d, t, true);
     const bool valid = score_current == score_current;
     if (active && !valid) atomicExch(K.error_flag, 1);
     const bool alive = active && valid;
 
     Rng rng;
     CellCache cc = cell_cache_of(d);
-    CandMasks masks = sh.m;
     // Every lane walks its own (stage, outer loop, inner step) schedule: replicas of one warp need
     // different numbers of scored proposals per inner loop (the in-bounds fraction depends on the
     // replica's cell), and synchronising at loop ends would leave the faster lanes idle there.  Only
     // the score phases below are warp-wide.
-    // Per-lane schedule state is kept small (the unrolled test block needs the registers): the
-    // stage's constants are re-read from the kernel parameters at loop ends, and only what every
-    // draw needs lives in registers (the inner-loop length, the step scale, the temperature).
     int stage = 0;
     bool done = !alive;
     double len0 = d.v[0], ratio0 = d.v[1], kt = 0., step_ratio = 1.0, score_start = score_current;
@@ -592,7 +672,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
         }
         if (!__any_sync(0xffffffffu, have)) break;
         // phase A (lanes holding a proposal): geometry and candidate generation
-        int candidates = 0;
+        TCands cands;
         double old_s = 0., old_c = 0.;
         const CellCache old_cc = cc;
         if (have) {
@@ -608,15 +688,16 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
             }
             if (slot <= 2) cc = cell_cache_of(d);
             if constexpr (KIND == CP_LJ) {
+                const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
                 new_score = t_lj_score<NI>(P, g, d, t, cc);
             } else {
-                t_build_geometry<KIND, NI>(P, g, d, t);
-                candidates = t_sweep<KIND, NI>(P, g, d, t, cc, masks);
+                t_place<KIND, NI, NS>(P, v, d, t);
+                t_sweep<KIND, NI, NS>(P, v, d, t, cc, cands);
             }
         }
         // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
         bool overlap = false;
-        if constexpr (KIND != CP_LJ) overlap = t_drain_warp<KIND, NI>(P, smem, sh.pool, masks, candidates);
+        if constexpr (KIND != CP_LJ) overlap = t_overlap_warp<KIND, NI, NS>(P, v, cands);
         // phase C: Metropolis decision
         if (have) {
             bool accepted;
@@ -648,39 +729,48 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     }
 }
 
-template <int KIND, int NI>
+template <int KIND, int NI, int NS>
 __global__ void __launch_bounds__(kThreadBlock)
 score_thread_kernel(const __grid_constant__ KProblem P, const double *dof, unsigned long long n, double *out) {
     extern __shared__ double smem[];
-    const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);
+    TView v{};
+    if constexpr (KIND != CP_LJ) {
+        v = thread_view<KIND, NI, NS>(smem, P);
+        thread_stage_constants<KIND, NI, NS>(v, P);
+    }
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
-    if (rep >= n) return;
+    const bool active = rep < n;
     Dof d;
 #pragma unroll
-    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = dof[rep * CP_MAX_DOF + i];
-    out[rep] = t_state_score<KIND, NI>(P, sh.g, sh.m, d, trig_of(d));
+    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = active ? dof[rep * CP_MAX_DOF + i] : P.dof[i];
+    const double s = t_state_score<KIND, NI, NS>(P, v, smem, d, trig_of(d), active);
+    if (active) out[rep] = s;
 }
 
-template <int KIND, int NI>
+template <int KIND, int NI, int NS>
 __global__ void __launch_bounds__(kThreadBlock)
 replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof, const cp_move *mv,
                      unsigned long long n_moves, unsigned long long n, cp_decision *out) {
     extern __shared__ double smem[];
-    const ThreadShared sh = thread_shared(smem, KIND, P.n_items, P.n_syms);
-    const TGeo g = sh.g;
+    TView v{};
+    if constexpr (KIND != CP_LJ) {
+        v = thread_view<KIND, NI, NS>(smem, P);
+        thread_stage_constants<KIND, NI, NS>(v, P);
+    }
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
-    if (rep >= n) return;
+    const bool active = rep < n;
     Dof d;
 #pragma unroll
-    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = init_dof[rep * CP_MAX_DOF + i];
+    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = active ? init_dof[rep * CP_MAX_DOF + i] : P.dof[i];
     Trig t;
     const int n_cell = n_cell_dof(P.family);
     const double len0 = d.v[0], ratio0 = d.v[1];
     cp_sincos(d.v[5], &t.st, &t.ct);
     cp_sincos(d.v[2], &t.sa, &t.ca);
-    double score_current = t_state_score<KIND, NI>(P, g, sh.m, d, t);
+    double score_current = t_state_score<KIND, NI, NS>(P, v, smem, d, t, active);
     for (unsigned long long m = 0; m < n_moves; ++m) {
-        const cp_move M = mv[rep * n_moves + m];
+        cp_move M{};
+        if (active) M = mv[rep * n_moves + m];
         const int slot = basis_to_slot((int)M.basis_index, n_cell);
         const double val = d.get(slot);
         double lo, hi;
@@ -689,12 +779,17 @@ replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof,
         D.in_bounds = 0;
         D.accepted = 0;
         D.new_score = __longlong_as_double(0x7FF8000000000000ll);
-        if (lo <= M.new_value && M.new_value <= hi) {
-            D.in_bounds = 1;
+        const bool in_bounds = active && lo <= M.new_value && M.new_value <= hi;
+        if (in_bounds) {
             d.set(slot, M.new_value);
             cp_sincos(d.v[5], &t.st, &t.ct);
             cp_sincos(d.v[2], &t.sa, &t.ca);
-            D.new_score = t_state_score<KIND, NI>(P, g, sh.m, d, t);
+        }
+        // warp-collective: lanes without an in-bounds proposal take part with no candidates
+        const double s = t_state_score<KIND, NI, NS>(P, v, smem, d, t, in_bounds);
+        if (in_bounds) {
+            D.in_bounds = 1;
+            D.new_score = s;
             if (accept_move(D.new_score, score_current, M.kt, M.threshold)) {
                 score_current = D.new_score;
                 D.accepted = 1;
@@ -705,7 +800,7 @@ replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof,
             }
         }
         D.score_current = score_current;
-        out[rep * n_moves + m] = D;
+        if (active) out[rep * n_moves + m] = D;
     }
 }
 

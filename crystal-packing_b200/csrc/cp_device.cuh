@@ -123,16 +123,18 @@ __device__ __forceinline__ void philox(unsigned long long ctr, unsigned long lon
 }
 
 template <int RNG>
-__device__ __forceinline__ void rng_begin_stage(Rng &r, unsigned long long seed,
+__device__ __forceinline__ void rng_begin_stage(Rng &r, unsigned long long seed_base,
                                                 unsigned long long replica, int n_basis) {
     r.range = (unsigned long long)n_basis;
     r.zone = ~0ull - ((0ull - r.range) % r.range);
     if (RNG == CP_RNG_PCG64MCG) {
-        pcg_seed(r, seed);
+        pcg_seed(r, seed_base + replica);  // seed = index for every stage (main.rs:229,239,249)
     } else {
+        // Philox: the key is the job's seed (the same for every replica, so the ten round keys are
+        // warp-uniform), the stream is selected by the global replica id in the counter's upper half
         r.lo = 0;         // draw-block counter; restarts every stage like the reference's re-seeding
         r.hi = replica;   // stream id
-        r.key = seed;
+        r.key = seed_base;
     }
 }
 
@@ -568,6 +570,35 @@ __device__ __forceinline__ Trig trig_of(const Dof &d) {
     cp_sincos(d.v[5], &t.st, &t.ct);
     cp_sincos(d.v[2], &t.sa, &t.ca);
     return t;
+}
+
+// one out-of-line copy of the transcendental functions for the thread kernels (instruction cache:
+// the kernels call them from several places, a few lanes at a time)
+struct SinCos {
+    double s, c;
+};
+static __device__ __noinline__ SinCos dev_sincos(double x) {
+    SinCos r;
+    cp_sincos(x, &r.s, &r.c);
+    return r;
+}
+static __device__ __noinline__ double dev_exp(double x) { return cp_exp(x); }
+
+// accept_move with the cheap cases decided first; the result is the same in every case:
+//   new > old                      -> accepted (optimisation.rs:66)
+//   kt == 0 (stages 1 and 3)       -> (new - old) / 0 is -inf or NaN: exp gives 0 (rejected: the
+//                                     threshold is never negative) or NaN (new == old; f64::min
+//                                     ignores it: surface 1, accepted since the threshold is < 1)
+//   (new - old) / kt < -745.13..   -> cp_exp returns exactly 0.0 there: rejected
+__device__ __forceinline__ bool accept_move_fast(double new_score, double old, double kt, double threshold) {
+    if (!(new_score == new_score)) return false;  // None
+    if (new_score > old) return true;
+    if (__double_as_longlong(kt) == 0ll) return new_score == old;  // +0.0 only: -0.0 flips the sign of the quotient
+    const double x = (new_score - old) / kt;
+    if (x < -7.45133219101941108420e+02) return false;
+    const double e = dev_exp(x);
+    const double surface = (e != e) ? 1.0 : (e < 1.0 ? e : 1.0);
+    return threshold < surface;
 }
 
 // MCOptimiser::accept_score (optimisation.rs:55-78) with the threshold already drawn

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kBlock) mc_kernel(const __grid_constant__ KPar
         const KStage S = K.stages[stage];
         // generate_basis(): the upper bounds of length and ratio are their values now (cell.rs:139-152)
         const double len0 = d.v[0], ratio0 = d.v[1];
-        rng_begin_stage<RNG>(rng, K.seed_base + replica, replica, n_basis);
+        rng_begin_stage<RNG>(rng, K.seed_base, replica, n_basis);
         double kt = S.kt_start, step_ratio = 1.0;
         int convergence_count = 0;
         const unsigned long long outer = S.inner ? S.steps / S.inner : 0ull;

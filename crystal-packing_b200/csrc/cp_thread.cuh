@@ -32,48 +32,49 @@ constexpr int kThreadBlock = 32;
 constexpr int kQueueCap = 96;  // component pairs waiting for their f64 evaluation, per warp
 
 // A shape-pair candidate of one replica: shape i against image (ix, iy) of shape j, |ix|, |iy| <= 3.
-// Bit q = (ix + 3) * 7 + (iy + 3) of the 64-bit word of the pair; the centre bit (ix = iy = 0)
+// Bit q = (iy + 3) * 7 + (ix + 3) of the 64-bit word of the pair; the centre bit (ix = iy = 0)
 // stands for the in-cell pair i < j, whose displacement to_cartesian(f_j + (0, 0)) is bit for bit
 // j's own Cartesian position (x + 0.0 == x), so one routine serves both kinds.
 constexpr int kCentreBit = 24;
-// the self images (i == j) come in mirror pairs t, -t: bits with iy > 0, or iy == 0 and ix > 0
-constexpr unsigned long long self_half_mask() {
-    unsigned long long m = 0;
-    for (int ix = -3; ix <= 3; ++ix)
-        for (int iy = -3; iy <= 3; ++iy)
-            if (iy > 0 || (iy == 0 && ix > 0)) m |= 1ull << ((ix + 3) * 7 + (iy + 3));
-    return m;
+// decodes a candidate bit into its image offsets
+__device__ __forceinline__ void image_of_bit(int q, int &ix, int &iy) {
+    const int row = (q * 37) >> 8;  // q / 7 for q < 49
+    iy = row - 3;
+    ix = q - row * 7 - 3;
 }
 
 // ---------------------------------------------------------------------------------- shared memory
 // One block = one warp.  Planes are [element][lane] so that a lane's own accesses are conflict-free
 // and any lane can read any replica's column (cooperative tests).
 //   f64 plane : 0 a, 1 b, 2 cos, 3 sin of the cell angle, 4 cos, 5 sin of the site angle, then per
-//               symmetry image s: 6 + 4s + {0 fx, 1 fy (wrapped fractional), 2 cx, 3 cy (Cartesian)}
+//               symmetry image s: 6 + 4s + {0 fx, 1 fy (wrapped fractional), 2 cx, 3 cy (Cartesian)},
+//               then the six DOFs of the current (accepted) state and their upper bounds for this
+//               stage, so that the draw loop reads "the DOF the RNG picked" with one indexed load
 //   f32 plane : per image s, per point p: x, y of the rotated point (relative to the image's centre)
-//   masks     : N (N - 1) / 2 pair words + 1 self word (u64)
-//   constants : the shape components and the symmetry operators (f64), for the f64 evaluations
+//   masks     : N (N - 1) / 2 pair words + 1 self word (u64); in registers for multiplicities 1, 2
+//   constants : the shape components, the symmetry operators and the lower bounds of the DOFs (f64)
 template <int KIND, int NI, int NS>
 struct TLayout {
     int n, N, NP;
     __host__ __device__ TLayout(int n_items, int n_syms)
         : n(NI > 0 ? NI : n_items), N(NS > 0 ? NS : n_syms), NP((KIND == CP_POLYGON && NI == 0) ? 2 * n : n) {}
-    __host__ __device__ int f64_elems() const { return 6 + 4 * N; }
+    __host__ __device__ int dof0() const { return 6 + 4 * N; }   // element of DOF 0; upper bounds follow at + 6
+    __host__ __device__ int f64_elems() const { return 18 + 4 * N; }
     __host__ __device__ int f32_elems() const { return 2 * N * NP; }
     __host__ __device__ int pairs() const { return N * (N - 1) / 2; }
-    __host__ __device__ int const_doubles() const { return n * 4 + N * 6; }
+    __host__ __device__ int const_doubles() const { return n * 4 + N * 6 + 6; }
     __host__ __device__ size_t bytes() const {
         return 8 * (size_t)(32 * f64_elems() + 32 * (pairs() + 1) + const_doubles()) + 4 * (size_t)(32 * f32_elems()) +
-               4 * (size_t)(40 + kQueueCap);
+               4 * (size_t)(64 + kQueueCap);
     }
 };
 
 struct TView {
     double *f64;                // plane base (lane 0)
     unsigned long long *masks;  // plane base
-    double *c_items, *c_syms;
+    double *c_items, *c_syms, *c_lo;
     float *f32;       // plane base
-    unsigned *pool;   // [0..31] entries, [32] hit flags
+    unsigned *pool;   // [0..31] entries, [32..63] hit flag of each lane's replica
     unsigned *queue;  // kQueueCap items
 };
 
@@ -85,9 +86,10 @@ __device__ __forceinline__ TView thread_view(double *smem, const KProblem &P) {
     v.masks = reinterpret_cast<unsigned long long *>(smem + 32 * L.f64_elems());
     v.c_items = smem + 32 * (L.f64_elems() + L.pairs() + 1);
     v.c_syms = v.c_items + L.n * 4;
-    v.f32 = reinterpret_cast<float *>(v.c_syms + L.N * 6);
+    v.c_lo = v.c_syms + L.N * 6;
+    v.f32 = reinterpret_cast<float *>(v.c_lo + 6);
     v.pool = reinterpret_cast<unsigned *>(v.f32 + 32 * L.f32_elems());
-    v.queue = v.pool + 40;
+    v.queue = v.pool + 64;
     return v;
 }
 
@@ -97,6 +99,10 @@ __device__ __forceinline__ void thread_stage_constants(const TView &v, const KPr
     const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
     for (int e = threadIdx.x; e < L.n * 4; e += kThreadBlock) v.c_items[e] = P.items[e >> 2][e & 3];
     for (int e = threadIdx.x; e < L.N * 6; e += kThreadBlock) v.c_syms[e] = P.syms[e / 6][e % 6];
+    if (threadIdx.x < 6) {  // lower bounds per slot (cell.rs:139-160, site.rs:69-88)
+        const int e = threadIdx.x;
+        v.c_lo[e] = e == 0 ? 0.01 : (e == 1 ? 0.1 : (e == 2 ? CP_PI / 4. : (e == 5 ? 0. : -0.5)));
+    }
     __syncwarp();
 }
 
@@ -159,12 +165,28 @@ __device__ __forceinline__ void t_place(const KProblem &P, const TView &v, const
     }
 }
 
-// candidates of one lane
+// candidates of one lane: the masks (registers for multiplicities 1 and 2, shared memory otherwise)
+// and the cursor that draws them
+template <int NS>
 struct TCands {
-    unsigned long long cur = 0;  // bits of the current word still to draw
-    int phase = -1;              // words: 0 .. P - 1 the pairs i < j, P .. P + N - 1 the self word once per shape
+    static constexpr bool kRegs = NS == 1 || NS == 2;
+    unsigned long long r0 = 0, r1 = 0;  // NS = 1: r0 = self word; NS = 2: r0 = pair (0, 1), r1 = self word
+    unsigned long long *sh = nullptr;   // this lane's column of the mask plane
+    unsigned long long cur = 0;         // bits of the current word still to draw
+    int phase = -1;                     // words: 0 .. P - 1 the pairs i < j, P .. P + N - 1 the self word once per shape
     int remaining = 0;
-    unsigned force = 0;          // a candidate sits within rounding of the 2R filter: no certificate is used
+    unsigned force = 0;                 // a candidate sits within rounding of the 2R filter: no certificate is used
+    __device__ __forceinline__ void st(int w, unsigned long long x) {
+        if constexpr (kRegs) {
+            if (w == 0) r0 = x; else r1 = x;
+        } else {
+            sh[w * 32] = x;
+        }
+    }
+    __device__ __forceinline__ unsigned long long ld(int w) const {
+        if constexpr (kRegs) return w == 0 ? r0 : r1;
+        else return sh[w * 32];
+    }
 };
 
 // (i << 2) | j of pair word w: pairs in the order (0,1),(0,2),..,(N-2,N-1)
@@ -173,81 +195,93 @@ __device__ __forceinline__ int pair_of_word(int w, int N) {
     return (int)((lut >> (4 * w)) & 15u);
 }
 
-// One row-and-column pruned sweep: images (ix, iy) of a shape at fractional (fx0, fy0) against a
-// shape at Cartesian (cx, cy).  A candidate passes the reference's filter when dx*dx + dy*dy <=
-// (2R)^2 (packed.rs:150-157); this sweep keeps everything up to (2R)^2 (1 + 1e-9) and reports whether
-// anything landed within 1e-9 of the threshold (the mirror image's distance differs by rounding).
-// Rows with |dy| beyond the reach and columns outside [(u - 2R)/a, (u + 2R)/a] (widened by 1e-6
-// columns) fail by margins >= 1e6 ulp; what is kept is evaluated with the reference's expressions.
-__device__ __forceinline__ unsigned long long t_sweep_pair(double cx, double cy, double fx0, double fy0, double a,
-                                                           double b, const Trig &t, const CellCache &cc, double r2x,
-                                                           bool self, unsigned &band) {
-    const int shells = cc.shells;
-    const double radius_sq = r2x * r2x;
-    const double wide = radius_sq * (1.0 + 1e-9), narrow = radius_sq * (1.0 - 1e-9);
-    const double row_reach = r2x * (1.0 + 1e-8);
-    const double w = r2x * cc.inv_a * (1.0 + 1e-8) + 1e-6;
+// The image sweep in single precision.  The reference keeps an image when dx*dx + dy*dy <= (2R)^2 in
+// f64 (packed.rs:150-157).  Here the displacement of image (ix, iy) is d0 + ix a + iy b from f32
+// copies of the lattice vectors; its error is below 2^-24 (|d0|_1 + 6 (|a| + |b|)), so with
+// delta = 2^-19 (|a| + |b|) / R + 2^-20 every image the reference keeps has d2 <= (2R)^2 (1 + delta)
+// here (those are the candidates), and an image with d2 <= (2R)^2 (1 - delta) here is kept by the
+// reference for certain.  Candidates in between set `band`: the lane's candidates then go through
+// the f64 path, which applies the reference's own filter.  Rows with |dy| beyond the reach are
+// skipped and only the columns that can reach are visited.
+struct TSweep {
+    float af, inv_af, bxf, byf;  // a = (af, 0), b = (bxf, byf)
+    float reach, wide2, narrow2;
+    int shells;
+};
+__device__ __forceinline__ TSweep t_sweep_setup(const KProblem &P, const Dof &d, const Trig &t, const CellCache &cc) {
+    TSweep s;
+    const double b = d.v[0] * d.v[1];
+    s.af = (float)d.v[0];
+    s.inv_af = (float)cc.inv_a;
+    s.bxf = (float)(b * t.ca);
+    s.byf = (float)(b * t.sa);
+    const float r2x = 2.0f * P.radf;
+    const float delta = fmaf(1.9073486328125e-06f, (s.af + fabsf(s.bxf) + fabsf(s.byf)) / P.radf, 9.5367431640625e-07f);
+    s.reach = r2x * (1.0f + delta);
+    s.wide2 = r2x * r2x * (1.0f + delta);
+    s.narrow2 = r2x * r2x * (1.0f - delta);
+    s.shells = cc.shells;
+    return s;
+}
+__device__ __forceinline__ unsigned long long t_sweep_pair(const TSweep &s, float d0x, float d0y, bool self,
+                                                           unsigned &band) {
     unsigned long long bits = 0ull;
-    // the image offsets as doubles, stepped by 1.0 (exact for these small integers)
-    double diy = self ? 0.0 : (double)(-shells);
-    for (int iy = self ? 0 : -shells; iy <= shells; ++iy, diy += 1.0) {
-        const double fy = fy0 + diy;  // to_cartesian_translate (cell.rs:241-245)
-        const double yb = fy * b;
-        const double ddy = cy - yb * t.sa;
-        if (fabs(ddy) > row_reach) continue;
-        const double ybca = yb * t.ca, ddy2 = ddy * ddy;
-        const double u = (cx - ybca) * cc.inv_a - fx0;  // column where dx would vanish
-        int lo = __double2int_ru(u - w), hi = __double2int_rd(u + w);
-        lo = lo < -shells ? -shells : lo;
-        hi = hi > shells ? shells : hi;
+    const float w = s.reach * s.inv_af + 1e-3f;
+    float fiy = self ? 0.0f : (float)(-s.shells);
+#pragma unroll 1
+    for (int iy = self ? 0 : -s.shells; iy <= s.shells; ++iy, fiy += 1.0f) {
+        const float vy = fmaf(fiy, s.byf, d0y);
+        if (fabsf(vy) > s.reach) continue;
+        const float x0 = fmaf(fiy, s.bxf, d0x), vy2 = vy * vy;
+        const float u = -x0 * s.inv_af;  // column where dx would vanish
+        int lo = __float2int_ru(u - w), hi = __float2int_rd(u + w);
+        lo = lo < -s.shells ? -s.shells : lo;
+        hi = hi > s.shells ? s.shells : hi;
         if (self && iy == 0 && lo < 1) lo = 1;
-        double dix = (double)lo;
-        for (int ix = lo; ix <= hi; ++ix, dix += 1.0) {
-            const double fx = fx0 + dix;
-            const double ddx = cx - (fx * a + ybca);
-            const double d2 = ddx * ddx + ddy2;
-            if (d2 <= wide && (ix | iy) != 0) {
-                bits |= 1ull << ((ix + 3) * 7 + (iy + 3));
-                if (!(d2 <= narrow)) band = 1u;
+        float fix = (float)lo;
+        unsigned row = 0u;
+#pragma unroll 1
+        for (int ix = lo; ix <= hi; ++ix, fix += 1.0f) {
+            const float vx = fmaf(fix, s.af, x0);
+            const float d2 = fmaf(vx, vx, vy2);
+            if (d2 <= s.wide2) {
+                row |= 1u << (ix + 3);
+                if (!(d2 <= s.narrow2)) band = 1u;
             }
         }
+        bits |= (unsigned long long)row << ((iy + 3) * 7);
     }
-    return bits;
+    return bits & ~(1ull << kCentreBit);  // the zero offset is not an image (cell.rs:216-225)
 }
 
 // Candidate generation for PackedState::check_intersection (state/packed.rs:127-167), half of the
 // ordered pairs: every in-cell pair i < j (no distance filter there, packed.rs:134-148), every
-// image of j against i for i < j, and the upper half of the self images (taken once, from shape 0:
-// the displacement is the lattice vector whichever the shape).  Returns the candidate count.
+// image of j against i for i < j, and the upper half of the self images (once for all shapes: the
+// displacement is the lattice vector whichever the shape).
 template <int KIND, int NI, int NS>
 __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const Dof &d, const Trig &t,
-                                        const CellCache &cc, TCands &c) {
+                                        const CellCache &cc, TCands<NS> &c) {
     const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
     const double *g = v.f64 + threadIdx.x;
-    unsigned long long *m = v.masks + threadIdx.x;
-    const double a = d.v[0], b = d.v[0] * d.v[1];
-    const double r2x = P.radius * 2.;
-    int count = 0, w = 0;
+    const TSweep s = t_sweep_setup(P, d, t, cc);
+    const int PW = L.pairs();
+    int count = 0;
     unsigned band = 0u;
-#pragma unroll
-    for (int i = 0; i < (NS > 0 ? NS : CP_MAX_SYMS); ++i) {
-        if (NS == 0 && i >= L.N) break;
-        const double cx = g[(6 + 4 * i + 2) * 32], cy = g[(6 + 4 * i + 3) * 32];
-#pragma unroll
-        for (int j = i + 1; j < (NS > 0 ? NS : CP_MAX_SYMS); ++j) {
-            if (NS == 0 && j >= L.N) break;
-            const unsigned long long bits =
-                t_sweep_pair(cx, cy, g[(6 + 4 * j + 0) * 32], g[(6 + 4 * j + 1) * 32], a, b, t, cc, r2x, false, band) |
-                (1ull << kCentreBit);
-            m[w * 32] = bits;
-            ++w;
-            count += __popcll(bits);
+    // one rolled loop over the pair words and the self word: a single copy of the sweep in the kernel
+#pragma unroll 1
+    for (int w = 0; w <= PW; ++w) {
+        const bool self = w == PW;
+        float d0x = 0.0f, d0y = 0.0f;
+        if (!self) {
+            const int ij = pair_of_word(w, L.N), i = ij >> 2, j = ij & 3;
+            d0x = (float)(g[(6 + 4 * j + 2) * 32] - g[(6 + 4 * i + 2) * 32]);
+            d0y = (float)(g[(6 + 4 * j + 3) * 32] - g[(6 + 4 * i + 3) * 32]);
         }
+        unsigned long long bits = t_sweep_pair(s, d0x, d0y, self, band);
+        if (!self) bits |= 1ull << kCentreBit;
+        c.st(w, bits);
+        count += __popcll(bits) * (self ? L.N : 1);
     }
-    const unsigned long long self =
-        t_sweep_pair(g[(6 + 2) * 32], g[(6 + 3) * 32], g[(6 + 0) * 32], g[(6 + 1) * 32], a, b, t, cc, r2x, true, band);
-    m[w * 32] = self;
-    count += L.N * __popcll(self);
     c.cur = 0;
     c.phase = -1;
     c.remaining = count;
@@ -255,10 +289,11 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
 }
 
 // draws the next candidate of this lane (remaining > 0 guarantees there is one)
-__device__ __forceinline__ void t_pop(TCands &c, const unsigned long long *m, int P, int N, int &ij, int &q) {
+template <int NS>
+__device__ __forceinline__ void t_pop(TCands<NS> &c, int P, int N, int &ij, int &q) {
     while (c.cur == 0ull) {
         ++c.phase;
-        c.cur = m[(c.phase < P ? c.phase : P) * 32];
+        c.cur = c.ld(c.phase < P ? c.phase : P);
     }
     q = __ffsll((long long)c.cur) - 1;
     c.cur &= c.cur - 1;
@@ -283,8 +318,8 @@ __device__ __noinline__ bool t_exact_item(const KProblem &P, const TView &v, uns
                  cyi = o[(6 + 4 * i + 3) * 32];
     const double fxj = o[(6 + 4 * j + 0) * 32], fyj = o[(6 + 4 * j + 1) * 32], cxj = o[(6 + 4 * j + 2) * 32],
                  cyj = o[(6 + 4 * j + 3) * 32];
-    const int qx = (q * 37) >> 8;  // q / 7 for q < 49
-    const int ix = qx - 3, iy = q - qx * 7 - 3;
+    int ix, iy;
+    image_of_bit(q, ix, iy);
     const bool incell = q == kCentreBit && i != j;
     const double r2x = P.radius * 2.;
     const double radius_sq = r2x * r2x;
@@ -349,16 +384,18 @@ __device__ __noinline__ bool t_exact_item(const KProblem &P, const TView &v, uns
 
 // evaluates the queued component pairs, one per lane; owners that already have a hit are skipped
 template <int KIND, int NI, int NS>
-__device__ __forceinline__ void t_flush(const KProblem &P, const TView &v, int qcount) {
+__device__ __noinline__ void t_flush(const KProblem &P, const TView &v, int qcount) {
     const unsigned lane = threadIdx.x & 31u;
     __syncwarp();
+#pragma unroll 1
     for (int base = 0; base < qcount; base += 32) {
         const int idx = base + (int)lane;
         if (idx < qcount) {
             const unsigned item = v.queue[idx];
             const unsigned owner = item >> 18;
-            if (!((*(volatile unsigned *)&v.pool[32] >> owner) & 1u))
-                if (t_exact_item<KIND, NI, NS>(P, v, item)) atomicOr(&v.pool[32], 1u << owner);
+            volatile unsigned *flag = v.pool + 32 + owner;
+            if (!*flag)
+                if (t_exact_item<KIND, NI, NS>(P, v, item)) *flag = 1u;
         }
     }
     __syncwarp();
@@ -368,19 +405,20 @@ __device__ __forceinline__ void t_flush(const KProblem &P, const TView &v, int q
 // PackedState::check_intersection for the 32 replicas of the warp at once (see the header comment).
 // Must be called by all 32 lanes converged; lanes without a proposal pass remaining = 0.
 template <int KIND, int NI, int NS>
-__device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v, TCands &c) {
+__device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v, TCands<NS> &c) {
     const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
     constexpr int W = NI > 0 ? cpf_words(NI) : CPF_MAX_WORDS;
     const unsigned lane = threadIdx.x & 31u;
     const int NP2 = L.NP * 2, PW = L.pairs(), nn = L.n * L.n;
-    const unsigned long long *my_masks = v.masks + lane;
     int qcount = 0;  // warp-uniform
-    if (lane == 0) v.pool[32] = 0u;
+    v.pool[32 + lane] = 0u;  // hit flag of this lane's replica: any lane may raise it (plain stores of 1)
     __syncwarp();
     for (;;) {
         const unsigned wanting = __ballot_sync(0xffffffffu, c.remaining > 0);
         if (wanting == 0u) break;
-        const int quota = 32 / __popc(wanting);  // >= 1; the pool never exceeds 32 entries
+        // 32 / (lanes wanting), >= 1: the pool never exceeds 32 entries (the quotient of floats is exact
+        // where it is an integer and at least 1/32 away from one otherwise)
+        const int quota = (int)__fdividef(32.0f, (float)__popc(wanting));
         const int take = c.remaining < quota ? c.remaining : quota;
         int incl = take;
 #pragma unroll
@@ -392,7 +430,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
         int slot = incl - take;
         for (int k = 0; k < take; ++k) {
             int ij, q;
-            t_pop(c, my_masks, PW, L.N, ij, q);
+            t_pop<NS>(c, PW, L.N, ij, q);
             v.pool[slot++] = (lane << 11) | (c.force << 10) | (unsigned)(ij << 6) | (unsigned)q;
         }
         c.remaining -= take;
@@ -406,8 +444,8 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
             const unsigned owner = entry >> 11, force = (entry >> 10) & 1u;
             const int i = (entry >> 8) & 3, j = (entry >> 6) & 3, q = entry & 63;
             const double *o = v.f64 + owner;
-            const int qx = (q * 37) >> 8;  // q / 7 for q < 49
-            const int ix = qx - 3, iy = q - qx * 7 - 3;
+            int ix, iy;
+            image_of_bit(q, ix, iy);
             // image position of shape j relative to shape i: to_cartesian_translate (cell.rs:241-245)
             const double a = o[0 * 32], b = o[1 * 32], ca = o[2 * 32], sa = o[3 * 32];
             const double fx = o[(6 + 4 * j + 0) * 32] + (double)ix, fy = o[(6 + 4 * j + 1) * 32] + (double)iy;
@@ -434,7 +472,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
                 }
                 count = nn;
             } else if (cmin < -tau) {
-                atomicOr(&v.pool[32], 1u << owner);  // certified: some component test is true
+                v.pool[32 + owner] = 1u;  // certified: some component test is true
             } else {
 #pragma unroll
                 for (int w = 0; w < W; ++w) count += __popc(amb[w]);
@@ -455,6 +493,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
                         unsigned bits = amb[w];
+#pragma unroll 1
                         while (bits && !h) {
                             const int p = 32 * w + __ffs((int)bits) - 1;
                             bits &= bits - 1;
@@ -462,7 +501,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
                             h = t_exact_item<KIND, NI, NS>(P, v, head | (unsigned)(l << 4) | (unsigned)k);
                         }
                     }
-                    if (h) atomicOr(&v.pool[32], 1u << (entry >> 11));
+                    if (h) v.pool[32 + (entry >> 11)] = 1u;
                 }
             } else {
                 int inc2 = count;
@@ -476,6 +515,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
                         unsigned bits = amb[w];
+#pragma unroll 1
                         while (bits) {
                             const int p = 32 * w + __ffs((int)bits) - 1;
                             bits &= bits - 1;
@@ -488,15 +528,14 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
             }
         }
         __syncwarp();
-        if ((v.pool[32] >> lane) & 1u) c.remaining = 0;  // decided: the rest of this replica's candidates need no test
+        if (v.pool[32 + lane]) c.remaining = 0;  // decided: the rest of this replica's candidates need no test
         __syncwarp();                                    // the pool is rewritten by the next round
     }
     if (qcount > 0) t_flush<KIND, NI, NS>(P, v, qcount);
-    return (v.pool[32] >> lane) & 1u;
+    return v.pool[32 + lane] != 0u;
 }
 
-// State::score for the warp's 32 replicas (batch score, replay, initial score); warp-collective.
-// LJ: everything is lane-local.
+// State::score for the warp's 32 replicas (batch score, replay); warp-collective.  LJ: lane-local.
 template <int KIND, int NI, int NS>
 __device__ __forceinline__ double t_state_score(const KProblem &P, const TView &v, double *smem, const Dof &d,
                                                 const Trig &t, bool live) {
@@ -504,7 +543,8 @@ __device__ __forceinline__ double t_state_score(const KProblem &P, const TView &
         const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
         return t_lj_score<NI>(P, g, d, t, cell_cache_of(d));
     } else {
-        TCands c;
+        TCands<NS> c;
+        c.sh = v.masks + threadIdx.x;
         if (live) {
             t_place<KIND, NI, NS>(P, v, d, t);
             t_sweep<KIND, NI, NS>(P, v, d, t, cell_cache_of(d), c);
@@ -526,10 +566,13 @@ __host__ __device__ inline size_t thread_block_shared_bytes(int n_items, int n_s
 // MCOptimiser::optimise_state (optimisation.rs:80-180) for every stage, seeds and bounds per stage
 // as analyse_state / generate_basis set them.
 // Register budget = minimum resident blocks per SM: 14 warps per SM hold all 2,048 warps of a
-// 65,536-replica batch at once (<= 146 registers).
+// 65,536-replica batch at once.
 constexpr int thread_min_blocks(int kind, int ni) {
     return kind == CP_LJ ? 10 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)));
 }
+// proposals a lane may draw per pass before the warp goes on to score what it has: the draw loop
+// is divergent (lanes leave it as they find a proposal worth scoring), so its tail is cut
+constexpr int kDrawCap = 4;
 
 template <int KIND, int NI, int NS, int RNG>
 __global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI))
@@ -537,10 +580,13 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
     TView v{};
+    int e_dof = 0;
     if constexpr (KIND != CP_LJ) {
         v = thread_view<KIND, NI, NS>(smem, P);
         thread_stage_constants<KIND, NI, NS>(v, P);
+        e_dof = TLayout<KIND, NI, NS>(P.n_items, P.n_syms).dof0();
     }
+    double *const mine = v.f64 + threadIdx.x;  // this lane's column of the f64 plane (hard shapes)
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
     const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
     const unsigned long long replica = K.replica_begin + (active ? rep : 0ull);
@@ -550,34 +596,42 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     for (int i = 0; i < CP_MAX_DOF; ++i)
         d.v[i] = (K.init_dof && active) ? K.init_dof[rep * CP_MAX_DOF + i] : P.dof[i];
     Trig t;
-    cp_sincos(d.v[5], &t.st, &t.ct);
-    cp_sincos(d.v[2], &t.sa, &t.ca);
-
+    {
+        const SinCos th = dev_sincos(d.v[5]), an = dev_sincos(d.v[2]);
+        t.st = th.s; t.ct = th.c; t.sa = an.s; t.ca = an.c;
+    }
     const int n_cell = n_cell_dof(P.family);
     const int n_basis = n_cell + 3;
+    const double area_n = P.area * (double)P.n_syms;  // numerator of packed.rs:84
     unsigned long long rejections = 0, moves = 0;
-    double score_current = t_state_score<KIND, NI, NS>(P, v, smem, d, t, true);
-    const bool valid = score_current == score_current;
-    if (active && !valid) atomicExch(K.error_flag, 1);
-    const bool alive = active && valid;
+    double score_current = 0.;
 
     Rng rng;
     CellCache cc = cell_cache_of(d);
+    TCands<NS> cands;
+    if constexpr (KIND != CP_LJ) cands.sh = v.masks + threadIdx.x;
     // Every lane walks its own (stage, outer loop, inner step) schedule: replicas of one warp need
     // different numbers of scored proposals per inner loop (the in-bounds fraction depends on the
     // replica's cell), and synchronising at loop ends would leave the faster lanes idle there.  Only
     // the score phases below are warp-wide.
-    int stage = 0;
-    bool done = !alive;
-    double len0 = d.v[0], ratio0 = d.v[1], kt = 0., step_ratio = 1.0, score_start = score_current;
+    int stage = -1;
+    bool done = !active;
+    double kt = 0., step_ratio = 1.0, score_start = 0.;
+    double len0 = d.v[0], ratio0 = d.v[1];  // LJ keeps the captured bounds in registers
     double step_scale = 0.;  // max_step_size * step_ratio, the loop-invariant factor of optimisation.rs:115-119
     int convergence_count = 0;
     unsigned long long inner = 0, loops_left = 0, it = 0, loop_rejections = 0;
     auto begin_stage = [&]() {
         const KStage &S = K.stages[stage];
-        len0 = d.v[0];  // generate_basis(): bounds captured per optimise_state call (cell.rs:139-152)
-        ratio0 = d.v[1];
-        rng_begin_stage<RNG>(rng, K.seed_base + replica, replica, n_basis);
+        // generate_basis(): bounds captured per optimise_state call (cell.rs:139-152)
+        if constexpr (KIND != CP_LJ) {
+            mine[(e_dof + 6 + 0) * 32] = d.v[0];
+            mine[(e_dof + 6 + 1) * 32] = d.v[1];
+        } else {
+            len0 = d.v[0];
+            ratio0 = d.v[1];
+        }
+        rng_begin_stage<RNG>(rng, K.seed_base, replica, n_basis);
         kt = S.kt_start;
         step_ratio = 1.0;
         step_scale = S.max_step * step_ratio;
@@ -599,92 +653,131 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
             if (loops_left > 0) return;
         }
     };
-    if (!done) {
-        stage = -1;
-        next_stage();
+    if constexpr (KIND != CP_LJ) {
+#pragma unroll
+        for (int i = 0; i < CP_MAX_DOF; ++i) mine[(e_dof + i) * 32] = d.v[i];
+        mine[(e_dof + 6 + 2) * 32] = CP_PI / 2.;  // the upper bounds that do not depend on the stage
+        mine[(e_dof + 6 + 3) * 32] = 0.5;
+        mine[(e_dof + 6 + 4) * 32] = 0.5;
+        mine[(e_dof + 6 + 5) * 32] = CP_TAU;
     }
+    // The first pass scores the initial state through the same code as every proposal
+    // (optimisation.rs:81-84: an invalid initial state is an error); `first` is warp-uniform.
+    bool first = true;
     for (;;) {
         bool have = false;
-        int slot = 0;
-        double val = 0., new_val = 0., threshold = 0., new_score = 0., new_s = 0., new_c = 0.;
-        // Draw until a proposal needs scoring.  Out-of-bounds proposals are rejected by
-        // Basis::set_value without a score (optimisation.rs:120-123).  For hard shapes the
-        // packing fraction depends on the cell DOFs only, so `Some(new_score)` is known
-        // before any overlap test: when the Metropolis rule would reject even a valid
-        // state (a cell move that lowers the score, lost against the threshold) the
-        // reference's answer is "rejected" whether check_intersection says None or Some,
-        // and the overlap test is skipped.  Draw order (index, step, threshold) and every
-        // decision are unchanged.
-        while (!done && !have) {
-            if (it == inner) {  // end of an inner loop (optimisation.rs:138-167)
-                const KStage &S = K.stages[stage];
-                moves += inner;
-                rejections += loop_rejections;
-                kt *= S.kt_ratio;
-                bool converged = false;
-                if (S.convergence == S.convergence) {
-                    if (score_current - score_start < S.convergence) {
-                        if (++convergence_count > 5) converged = true;
-                    } else {
-                        convergence_count = 0;
+        int slot = 6;  // 6 = no DOF changes (the first pass)
+        double val = 0., new_val = 0., threshold = 0., new_score = 0.;
+        if (first) {
+            have = true;  // tail lanes score the template state too: their result is never written
+        } else {
+            // Draw until a proposal needs scoring, at most kDrawCap draws per pass.  Out-of-bounds
+            // proposals are rejected by Basis::set_value without a score (optimisation.rs:120-123).
+            // For hard shapes the packing fraction depends on the cell DOFs only, so
+            // `Some(new_score)` is known before any overlap test: when the Metropolis rule would
+            // reject even a valid state (a cell move that lowers the score, lost against the
+            // threshold) the reference's answer is "rejected" whether check_intersection says None or
+            // Some, and the overlap test is skipped.  Draw order (index, step, threshold) and every
+            // decision are unchanged.
+            for (int draws = 0; draws < kDrawCap && !done && !have; ++draws) {
+                if (it == inner) {  // end of an inner loop (optimisation.rs:138-167)
+                    const KStage &S = K.stages[stage];
+                    moves += inner;
+                    rejections += loop_rejections;
+                    kt *= S.kt_ratio;
+                    bool converged = false;
+                    if (S.convergence == S.convergence) {
+                        if (score_current - score_start < S.convergence) {
+                            if (++convergence_count > 5) converged = true;
+                        } else {
+                            convergence_count = 0;
+                        }
                     }
+                    if (!converged && step_ratio > 1e-4)
+                        step_ratio *= (double)inner / ((double)loop_rejections + 1.);
+                    step_scale = S.max_step * step_ratio;
+                    --loops_left;
+                    it = 0;
+                    loop_rejections = 0;
+                    score_start = score_current;
+                    if (converged || loops_left == 0) next_stage();
+                    continue;
                 }
-                if (!converged && step_ratio > 1e-4)
-                    step_ratio *= (double)inner / ((double)loop_rejections + 1.);
-                step_scale = S.max_step * step_ratio;
-                --loops_left;
-                it = 0;
-                loop_rejections = 0;
-                score_start = score_current;
-                if (converged || loops_left == 0) next_stage();
-                continue;
-            }
-            ++it;
-            int basis_index;
-            double sample;
-            rng_draw_move<RNG>(rng, basis_index, sample);
-            slot = basis_to_slot(basis_index, n_cell);
-            val = d.get(slot);
-            new_val = val + step_scale * sample;
-            double lo, hi;
-            slot_bounds(slot, len0, ratio0, lo, hi);
-            have = lo <= new_val && new_val <= hi;
-            if (!have) {
-                ++loop_rejections;
-                continue;
-            }
-            if constexpr (KIND != CP_LJ) {
-                threshold = rng_draw_threshold<RNG>(rng);
-                new_score = score_current;  // site moves leave the packing fraction as it is
-                if (slot <= 2) {
-                    double sa_new = t.sa;
-                    if (slot == 2) {
-                        cp_sincos(new_val, &new_s, &new_c);
-                        sa_new = new_s;
+                ++it;
+                int basis_index;
+                double sample;
+                rng_draw_move<RNG>(rng, basis_index, sample);
+                slot = basis_to_slot(basis_index, n_cell);
+                double lo, hi;
+                if constexpr (KIND != CP_LJ) {
+                    val = mine[(e_dof + slot) * 32];
+                    hi = mine[(e_dof + 6 + slot) * 32];
+                    lo = v.c_lo[slot];
+                } else {
+                    val = d.get(slot);
+                    slot_bounds(slot, len0, ratio0, lo, hi);
+                }
+                new_val = val + step_scale * sample;
+                have = lo <= new_val && new_val <= hi;
+                if (!have) {
+                    ++loop_rejections;
+                    continue;
+                }
+                if constexpr (KIND != CP_LJ) {
+                    threshold = rng_draw_threshold<RNG>(rng);
+                    new_score = score_current;  // site moves leave the packing fraction as it is
+                    if (slot <= 2) {
+                        double sa_new = t.sa;
+                        bool settled = false;
+                        if (slot == 2) {
+                            // Cell-angle move.  A single-precision sine (absolute error < 2^-21 on this
+                            // range; margin 4e-6) settles the two common outcomes without the f64
+                            // sine: the area shrinks by a relative 2e-6 or more, so new > old and the
+                            // move is accepted whatever the temperature (the exact sine and score are
+                            // taken in phase A); or it grows that much while kT is +0 (stages 1 and
+                            // 3), where exp(-inf) = 0 rejects.  Everything else takes the exact path.
+                            const float s_old = (float)t.sa, s_new = __sinf((float)new_val);
+                            if (s_new < s_old * (1.0f - 4.0e-6f)) {
+                                settled = true;
+                            } else if (s_new > s_old * (1.0f + 4.0e-6f) && __double_as_longlong(kt) == 0ll) {
+                                settled = true;
+                                have = false;
+                            } else {
+                                sa_new = dev_sincos(new_val).s;
+                            }
+                        }
+                        if (!settled) {
+                            const double len = slot == 0 ? new_val : d.v[0], ratio = slot == 1 ? new_val : d.v[1];
+                            const double cell_area = sa_new * len * (len * ratio);  // cell.rs:190-192
+                            new_score = area_n / cell_area;                         // packed.rs:84
+                            have = accept_move_fast(new_score, score_current, kt, threshold);
+                        }
+                        if (!have) ++loop_rejections;
                     }
-                    const double len = slot == 0 ? new_val : d.v[0], ratio = slot == 1 ? new_val : d.v[1];
-                    const double cell_area = sa_new * len * (len * ratio);  // cell.rs:190-192
-                    new_score = (P.area * (double)P.n_syms) / cell_area;    // packed.rs:84
-                    have = accept_move(new_score, score_current, kt, threshold);
-                    if (!have) ++loop_rejections;
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, have)) break;
+        if (!__any_sync(0xffffffffu, have)) {
+            if (__all_sync(0xffffffffu, done)) break;
+            continue;  // every lane used up its draws without a proposal to score
+        }
         // phase A (lanes holding a proposal): geometry and candidate generation
-        TCands cands;
         double old_s = 0., old_c = 0.;
         const CellCache old_cc = cc;
+        cands.remaining = 0;
         if (have) {
             d.set(slot, new_val);
-            if (slot == 5) {  // the site angle and the cell angle are the only DOFs inside sin/cos
-                old_s = t.st; old_c = t.ct;
-                cp_sincos(new_val, &t.st, &t.ct);
-            }
-            if (slot == 2) {
-                old_s = t.sa; old_c = t.ca;
-                if constexpr (KIND == CP_LJ) cp_sincos(new_val, &new_s, &new_c);
-                t.sa = new_s; t.ca = new_c;
+            if (slot == 2 || slot == 5) {  // the cell angle and the site angle are the only DOFs inside sin/cos
+                const SinCos sc = dev_sincos(new_val);
+                if (slot == 5) {
+                    old_s = t.st; old_c = t.ct;
+                    t.st = sc.s; t.ct = sc.c;
+                } else {
+                    old_s = t.sa; old_c = t.ca;
+                    t.sa = sc.s; t.ca = sc.c;
+                    if constexpr (KIND != CP_LJ)
+                        new_score = area_n / (t.sa * d.v[0] * (d.v[0] * d.v[1]));  // cell.rs:190-192, packed.rs:84
+                }
             }
             if (slot <= 2) cc = cell_cache_of(d);
             if constexpr (KIND == CP_LJ) {
@@ -699,16 +792,27 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
         bool overlap = false;
         if constexpr (KIND != CP_LJ) overlap = t_overlap_warp<KIND, NI, NS>(P, v, cands);
         // phase C: Metropolis decision
-        if (have) {
+        if (first) {
+            if constexpr (KIND != CP_LJ)
+                new_score = overlap ? __longlong_as_double(0x7FF8000000000000ll)
+                                    : area_n / (t.sa * d.v[0] * (d.v[0] * d.v[1]));
+            score_current = new_score;
+            const bool valid = score_current == score_current;
+            if (active && !valid) atomicExch(K.error_flag, 1);
+            if (!valid) done = true;
+            if (!done) next_stage();
+            first = false;
+        } else if (have) {
             bool accepted;
             if constexpr (KIND == CP_LJ) {
                 threshold = rng_draw_threshold<RNG>(rng);
-                accepted = accept_move(new_score, score_current, kt, threshold);
+                accepted = accept_move_fast(new_score, score_current, kt, threshold);
             } else {
                 accepted = !overlap;  // the rule itself was evaluated before the overlap test
             }
             if (accepted) {
                 score_current = new_score;
+                if constexpr (KIND != CP_LJ) mine[(e_dof + slot) * 32] = new_val;
             } else {
                 d.set(slot, val);
                 if (slot == 5) { t.st = old_s; t.ct = old_c; }

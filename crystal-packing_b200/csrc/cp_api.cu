@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -315,6 +316,11 @@ cp_status cp_prepare(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *
     K.seed_base = seed_base;
     K.replica_begin = replica_begin;
     K.n_replicas = n_replicas;
+    K.draw_cap = 4;
+    if (const char *e = std::getenv("CP_DRAW_CAP")) {  // tuning knob, see cp_thread.cuh
+        const int c = std::atoi(e);
+        if (c >= 1 && c <= 64) K.draw_cap = c;
+    }
     CP_CUDA(cudaSetDevice(ctx->device));
     if (ctx->cap_out < n_replicas) {
         cudaFree(ctx->d_out);

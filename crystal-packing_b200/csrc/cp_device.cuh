@@ -59,6 +59,7 @@ struct KParams {
     const double *init_dof;  // nullable: n_replicas x 6
     cp_replica_result *out;
     int *error_flag;
+    int draw_cap;  // thread kernels: proposals a lane may draw per pass (cp_thread.cuh)
 };
 
 // ------------------------------------------------------------------------------------------ RNG
@@ -170,6 +171,17 @@ __device__ __forceinline__ void rng_draw_move(Rng &r, int &basis_index, double &
         const unsigned spare = (unsigned)(((a & 0xFFFull) << 11) | (b & 0x7FFull));
         basis_index = (int)((spare * (unsigned)r.range) >> 23);
         sample = u64_to_step(a);
+    }
+}
+
+// draw #3 as raw bits: the conversion to [0, 1) is needed only where the Metropolis rule gets as
+// far as comparing against the threshold
+template <int RNG>
+__device__ __forceinline__ unsigned long long rng_draw_threshold_bits(Rng &r) {
+    if (RNG == CP_RNG_PCG64MCG) {
+        return pcg_next(r);
+    } else {
+        return r.thr;
     }
 }
 
@@ -590,7 +602,7 @@ static __device__ __noinline__ double dev_exp(double x) { return cp_exp(x); }
 //                                     threshold is never negative) or NaN (new == old; f64::min
 //                                     ignores it: surface 1, accepted since the threshold is < 1)
 //   (new - old) / kt < -745.13..   -> cp_exp returns exactly 0.0 there: rejected
-__device__ __forceinline__ bool accept_move_fast(double new_score, double old, double kt, double threshold) {
+__device__ __forceinline__ bool accept_move_fast(double new_score, double old, double kt, unsigned long long threshold_bits) {
     if (!(new_score == new_score)) return false;  // None
     if (new_score > old) return true;
     if (__double_as_longlong(kt) == 0ll) return new_score == old;  // +0.0 only: -0.0 flips the sign of the quotient
@@ -598,7 +610,7 @@ __device__ __forceinline__ bool accept_move_fast(double new_score, double old, d
     if (x < -7.45133219101941108420e+02) return false;
     const double e = dev_exp(x);
     const double surface = (e != e) ? 1.0 : (e < 1.0 ? e : 1.0);
-    return threshold < surface;
+    return u64_to_unit(threshold_bits) < surface;
 }
 
 // MCOptimiser::accept_score (optimisation.rs:55-78) with the threshold already drawn

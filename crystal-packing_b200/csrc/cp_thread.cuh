@@ -50,7 +50,8 @@ __device__ __forceinline__ void image_of_bit(int q, int &ix, int &iy) {
 //               symmetry image s: 6 + 4s + {0 fx, 1 fy (wrapped fractional), 2 cx, 3 cy (Cartesian)},
 //               then the six DOFs of the current (accepted) state and their upper bounds for this
 //               stage, so that the draw loop reads "the DOF the RNG picked" with one indexed load
-//   f32 plane : per image s, per point p: x, y of the rotated point (relative to the image's centre)
+//   f32 plane : per image s, per point p: x, y of the rotated point (relative to the image's centre);
+//               last element: the squared distance below which an image is a candidate for certain
 //   masks     : N (N - 1) / 2 pair words + 1 self word (u64); in registers for multiplicities 1, 2
 //   constants : the shape components, the symmetry operators and the lower bounds of the DOFs (f64)
 template <int KIND, int NI, int NS>
@@ -64,8 +65,8 @@ struct TLayout {
     __host__ __device__ int pairs() const { return N * (N - 1) / 2; }
     __host__ __device__ int const_doubles() const { return n * 4 + N * 6 + 6; }
     __host__ __device__ size_t bytes() const {
-        return 8 * (size_t)(32 * f64_elems() + 32 * (pairs() + 1) + const_doubles()) + 4 * (size_t)(32 * f32_elems()) +
-               4 * (size_t)(64 + kQueueCap);
+        return 8 * (size_t)(32 * f64_elems() + 32 * (pairs() + 1) + const_doubles()) + 4 * (size_t)(32 * (f32_elems() + 1)) +
+               4 * (size_t)(72 + kQueueCap);
     }
 };
 
@@ -74,7 +75,7 @@ struct TView {
     unsigned long long *masks;  // plane base
     double *c_items, *c_syms, *c_lo;
     float *f32;       // plane base
-    unsigned *pool;   // [0..31] entries, [32..63] hit flag of each lane's replica
+    unsigned *pool;   // [0..31] entries, [32..63] hit flag of each lane's replica, [64] queue fill
     unsigned *queue;  // kQueueCap items
 };
 
@@ -88,8 +89,8 @@ __device__ __forceinline__ TView thread_view(double *smem, const KProblem &P) {
     v.c_syms = v.c_items + L.n * 4;
     v.c_lo = v.c_syms + L.N * 6;
     v.f32 = reinterpret_cast<float *>(v.c_lo + 6);
-    v.pool = reinterpret_cast<unsigned *>(v.f32 + 32 * L.f32_elems());
-    v.queue = v.pool + 64;
+    v.pool = reinterpret_cast<unsigned *>(v.f32 + 32 * (L.f32_elems() + 1));
+    v.queue = v.pool + 72;
     return v;
 }
 
@@ -175,7 +176,6 @@ struct TCands {
     unsigned long long cur = 0;         // bits of the current word still to draw
     int phase = -1;                     // words: 0 .. P - 1 the pairs i < j, P .. P + N - 1 the self word once per shape
     int remaining = 0;
-    unsigned force = 0;                 // a candidate sits within rounding of the 2R filter: no certificate is used
     __device__ __forceinline__ void st(int w, unsigned long long x) {
         if constexpr (kRegs) {
             if (w == 0) r0 = x; else r1 = x;
@@ -199,59 +199,56 @@ __device__ __forceinline__ int pair_of_word(int w, int N) {
 // f64 (packed.rs:150-157).  Here the displacement of image (ix, iy) is d0 + ix a + iy b from f32
 // copies of the lattice vectors; its error is below 2^-24 (|d0|_1 + 6 (|a| + |b|)), so with
 // delta = 2^-19 (|a| + |b|) / R + 2^-20 every image the reference keeps has d2 <= (2R)^2 (1 + delta)
-// here (those are the candidates), and an image with d2 <= (2R)^2 (1 - delta) here is kept by the
-// reference for certain.  Candidates in between set `band`: the lane's candidates then go through
-// the f64 path, which applies the reference's own filter.  Rows with |dy| beyond the reach are
-// skipped and only the columns that can reach are visited.
+// here: those are the candidates.  Whether a candidate is one the reference keeps FOR CERTAIN is
+// decided where its certificate is evaluated (t_overlap_warp), from the f64 displacement, against
+// (2R)^2 (1 - delta) kept in the f32 plane.
+// All 48 offsets of three shells are evaluated in straight-line code (four instructions each, no
+// branches): in the packings the optimiser converges to, the cells are skewed enough that
+// periodic_range is 3 for nine moves out of ten (packed.rs:128-132), and loops over the few offsets
+// in reach cost more in branch latency than they save.
 struct TSweep {
-    float af, inv_af, bxf, byf;  // a = (af, 0), b = (bxf, byf)
-    float reach, wide2, narrow2;
+    float af, bxf, byf;  // a = (af, 0), b = (bxf, byf)
+    float wide2, narrow2;
     int shells;
 };
 __device__ __forceinline__ TSweep t_sweep_setup(const KProblem &P, const Dof &d, const Trig &t, const CellCache &cc) {
     TSweep s;
     const double b = d.v[0] * d.v[1];
     s.af = (float)d.v[0];
-    s.inv_af = (float)cc.inv_a;
     s.bxf = (float)(b * t.ca);
     s.byf = (float)(b * t.sa);
     const float r2x = 2.0f * P.radf;
     const float delta = fmaf(1.9073486328125e-06f, (s.af + fabsf(s.bxf) + fabsf(s.byf)) / P.radf, 9.5367431640625e-07f);
-    s.reach = r2x * (1.0f + delta);
     s.wide2 = r2x * r2x * (1.0f + delta);
     s.narrow2 = r2x * r2x * (1.0f - delta);
     s.shells = cc.shells;
     return s;
 }
-__device__ __forceinline__ unsigned long long t_sweep_pair(const TSweep &s, float d0x, float d0y, bool self,
-                                                           unsigned &band) {
-    unsigned long long bits = 0ull;
-    const float w = s.reach * s.inv_af + 1e-3f;
-    float fiy = self ? 0.0f : (float)(-s.shells);
-#pragma unroll 1
-    for (int iy = self ? 0 : -s.shells; iy <= s.shells; ++iy, fiy += 1.0f) {
-        const float vy = fmaf(fiy, s.byf, d0y);
-        if (fabsf(vy) > s.reach) continue;
-        const float x0 = fmaf(fiy, s.bxf, d0x), vy2 = vy * vy;
-        const float u = -x0 * s.inv_af;  // column where dx would vanish
-        int lo = __float2int_ru(u - w), hi = __float2int_rd(u + w);
-        lo = lo < -s.shells ? -s.shells : lo;
-        hi = hi > s.shells ? s.shells : hi;
-        if (self && iy == 0 && lo < 1) lo = 1;
-        float fix = (float)lo;
+template <bool SELF>
+__device__ __forceinline__ unsigned long long t_sweep_pair(const TSweep &s, float d0x, float d0y) {
+    const bool ring2 = s.shells >= 2, ring3 = s.shells >= 3;
+    unsigned lo = 0u, hi = 0u;
+#pragma unroll
+    for (int iy = SELF ? 0 : -3; iy <= 3; ++iy) {
+        const float vy = fmaf((float)iy, s.byf, d0y), x0 = fmaf((float)iy, s.bxf, d0x);
+        const float vy2 = vy * vy;
         unsigned row = 0u;
-#pragma unroll 1
-        for (int ix = lo; ix <= hi; ++ix, fix += 1.0f) {
-            const float vx = fmaf(fix, s.af, x0);
+#pragma unroll
+        for (int ix = (SELF && iy == 0) ? 1 : -3; ix <= 3; ++ix) {
+            if (ix == 0 && iy == 0) continue;  // the zero offset is not an image (cell.rs:216-225)
+            const int ring = (ix < 0 ? -ix : ix) > (iy < 0 ? -iy : iy) ? (ix < 0 ? -ix : ix) : (iy < 0 ? -iy : iy);
+            const float vx = fmaf((float)ix, s.af, x0);
             const float d2 = fmaf(vx, vx, vy2);
-            if (d2 <= s.wide2) {
-                row |= 1u << (ix + 3);
-                if (!(d2 <= s.narrow2)) band = 1u;
-            }
+            bool in = d2 <= s.wide2;
+            if (ring == 2) in = in && ring2;
+            if (ring == 3) in = in && ring3;
+            row |= in ? 1u << (ix + 3) : 0u;
         }
-        bits |= (unsigned long long)row << ((iy + 3) * 7);
+        const int sh = (iy + 3) * 7;  // row iy occupies bits sh .. sh + 6
+        if (sh < 32) lo |= row << sh;
+        if (sh + 7 > 32) hi |= sh >= 32 ? row << (sh - 32) : row >> (32 - sh);
     }
-    return bits & ~(1ull << kCentreBit);  // the zero offset is not an image (cell.rs:216-225)
+    return ((unsigned long long)hi << 32) | lo;
 }
 
 // Candidate generation for PackedState::check_intersection (state/packed.rs:127-167), half of the
@@ -264,28 +261,25 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
     const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
     const double *g = v.f64 + threadIdx.x;
     const TSweep s = t_sweep_setup(P, d, t, cc);
+    v.f32[L.f32_elems() * 32 + threadIdx.x] = s.narrow2;
     const int PW = L.pairs();
     int count = 0;
-    unsigned band = 0u;
-    // one rolled loop over the pair words and the self word: a single copy of the sweep in the kernel
+    // a rolled loop over the pair words: a single copy of the 48-offset sweep in the kernel
 #pragma unroll 1
-    for (int w = 0; w <= PW; ++w) {
-        const bool self = w == PW;
-        float d0x = 0.0f, d0y = 0.0f;
-        if (!self) {
-            const int ij = pair_of_word(w, L.N), i = ij >> 2, j = ij & 3;
-            d0x = (float)(g[(6 + 4 * j + 2) * 32] - g[(6 + 4 * i + 2) * 32]);
-            d0y = (float)(g[(6 + 4 * j + 3) * 32] - g[(6 + 4 * i + 3) * 32]);
-        }
-        unsigned long long bits = t_sweep_pair(s, d0x, d0y, self, band);
-        if (!self) bits |= 1ull << kCentreBit;
+    for (int w = 0; w < PW; ++w) {
+        const int ij = pair_of_word(w, L.N), i = ij >> 2, j = ij & 3;
+        const float d0x = (float)(g[(6 + 4 * j + 2) * 32] - g[(6 + 4 * i + 2) * 32]);
+        const float d0y = (float)(g[(6 + 4 * j + 3) * 32] - g[(6 + 4 * i + 3) * 32]);
+        const unsigned long long bits = t_sweep_pair<false>(s, d0x, d0y) | (1ull << kCentreBit);
         c.st(w, bits);
-        count += __popcll(bits) * (self ? L.N : 1);
+        count += __popcll(bits);
     }
+    const unsigned long long self = t_sweep_pair<true>(s, 0.0f, 0.0f);
+    c.st(PW, self);
+    count += __popcll(self) * L.N;
     c.cur = 0;
     c.phase = -1;
     c.remaining = count;
-    c.force = band;
 }
 
 // draws the next candidate of this lane (remaining > 0 guarantees there is one)
@@ -412,6 +406,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
     const int NP2 = L.NP * 2, PW = L.pairs(), nn = L.n * L.n;
     int qcount = 0;  // warp-uniform
     v.pool[32 + lane] = 0u;  // hit flag of this lane's replica: any lane may raise it (plain stores of 1)
+    if (lane == 0) v.pool[64] = 0u;
     __syncwarp();
     for (;;) {
         const unsigned wanting = __ballot_sync(0xffffffffu, c.remaining > 0);
@@ -431,7 +426,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
         for (int k = 0; k < take; ++k) {
             int ij, q;
             t_pop<NS>(c, PW, L.N, ij, q);
-            v.pool[slot++] = (lane << 11) | (c.force << 10) | (unsigned)(ij << 6) | (unsigned)q;
+            v.pool[slot++] = (lane << 11) | (unsigned)(ij << 6) | (unsigned)q;
         }
         c.remaining -= take;
         __syncwarp();
@@ -441,7 +436,7 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
         unsigned entry = 0u;
         if ((int)lane < total) {
             entry = v.pool[lane];
-            const unsigned owner = entry >> 11, force = (entry >> 10) & 1u;
+            const unsigned owner = entry >> 11;
             const int i = (entry >> 8) & 3, j = (entry >> 6) & 3, q = entry & 63;
             const double *o = v.f64 + owner;
             int ix, iy;
@@ -453,6 +448,9 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
             const float dX = (float)((fx * a + yb * ca) - o[(6 + 4 * i + 2) * 32]);
             const float dY = (float)(yb * sa - o[(6 + 4 * i + 3) * 32]);
             const TPts A{v.f32 + owner + (i * NP2) * 32, P.discrf}, B{v.f32 + owner + (j * NP2) * 32, P.discrf};
+            // an image within rounding of the reference's 2R filter (or beyond it): candidacy itself is
+            // in doubt, so no certificate is used and the f64 path applies the reference's own filter
+            const bool force = q != kCentreBit && !(fmaf(dX, dX, dY * dY) <= v.f32[L.f32_elems() * 32 + owner]);
             float cmin, tau;
             if constexpr (KIND == CP_POLYGON) {
                 tau = cpf_tau(P.radf, dX, dY);
@@ -484,6 +482,8 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
             if (qcount + fresh > kQueueCap) {
                 t_flush<KIND, NI, NS>(P, v, qcount);
                 qcount = 0;
+                if (lane == 0) v.pool[64] = 0u;
+                __syncwarp();
             }
             const unsigned head = (entry >> 11) << 18 | ((entry >> 6) & 15u) << 14 | (entry & 63u) << 8;
             if (fresh > kQueueCap) {
@@ -504,14 +504,8 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
                     if (h) v.pool[32 + (entry >> 11)] = 1u;
                 }
             } else {
-                int inc2 = count;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int up = __shfl_up_sync(0xffffffffu, inc2, o);
-                    if ((int)lane >= o) inc2 += up;
-                }
-                int at = qcount + inc2 - count;
                 if (count > 0) {
+                    int at = (int)atomicAdd(&v.pool[64], (unsigned)count);  // few lanes have any: no scan
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
                         unsigned bits = amb[w];
@@ -572,7 +566,7 @@ constexpr int thread_min_blocks(int kind, int ni) {
 }
 // proposals a lane may draw per pass before the warp goes on to score what it has: the draw loop
 // is divergent (lanes leave it as they find a proposal worth scoring), so its tail is cut
-constexpr int kDrawCap = 4;
+constexpr int kDrawCap = 4;  // default; KParams::draw_cap
 
 template <int KIND, int NI, int NS, int RNG>
 __global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI))
@@ -667,7 +661,8 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     for (;;) {
         bool have = false;
         int slot = 6;  // 6 = no DOF changes (the first pass)
-        double val = 0., new_val = 0., threshold = 0., new_score = 0.;
+        double val = 0., new_val = 0., new_score = 0.;
+        unsigned long long threshold = 0ull;  // raw bits of draw #3
         if (first) {
             have = true;  // tail lanes score the template state too: their result is never written
         } else {
@@ -679,7 +674,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
             // threshold) the reference's answer is "rejected" whether check_intersection says None or
             // Some, and the overlap test is skipped.  Draw order (index, step, threshold) and every
             // decision are unchanged.
-            for (int draws = 0; draws < kDrawCap && !done && !have; ++draws) {
+            for (int draws = 0; draws < K.draw_cap && !done && !have; ++draws) {
                 if (it == inner) {  // end of an inner loop (optimisation.rs:138-167)
                     const KStage &S = K.stages[stage];
                     moves += inner;
@@ -724,7 +719,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
                     continue;
                 }
                 if constexpr (KIND != CP_LJ) {
-                    threshold = rng_draw_threshold<RNG>(rng);
+                    threshold = rng_draw_threshold_bits<RNG>(rng);
                     new_score = score_current;  // site moves leave the packing fraction as it is
                     if (slot <= 2) {
                         double sa_new = t.sa;
@@ -805,7 +800,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
         } else if (have) {
             bool accepted;
             if constexpr (KIND == CP_LJ) {
-                threshold = rng_draw_threshold<RNG>(rng);
+                threshold = rng_draw_threshold_bits<RNG>(rng);
                 accepted = accept_move_fast(new_score, score_current, kt, threshold);
             } else {
                 accepted = !overlap;  // the rule itself was evaluated before the overlap test

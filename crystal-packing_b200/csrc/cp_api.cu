@@ -316,7 +316,9 @@ cp_status cp_prepare(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *
     K.seed_base = seed_base;
     K.replica_begin = replica_begin;
     K.n_replicas = n_replicas;
-    K.draw_cap = 4;
+    K.draw_cap = 3;
+    K.tune = 0;
+    if (const char *e = std::getenv("CP_TUNE")) K.tune = std::atoi(e);
     if (const char *e = std::getenv("CP_DRAW_CAP")) {  // tuning knob, see cp_thread.cuh
         const int c = std::atoi(e);
         if (c >= 1 && c <= 64) K.draw_cap = c;

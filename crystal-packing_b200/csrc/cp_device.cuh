@@ -60,6 +60,7 @@ struct KParams {
     cp_replica_result *out;
     int *error_flag;
     int draw_cap;  // thread kernels: proposals a lane may draw per pass (cp_thread.cuh)
+    int tune;      // experiment switches (CP_TUNE)
 };
 
 // ------------------------------------------------------------------------------------------ RNG

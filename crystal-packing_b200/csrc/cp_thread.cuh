@@ -36,6 +36,8 @@ constexpr int kQueueCap = 96;  // component pairs waiting for their f64 evaluati
 // stands for the in-cell pair i < j, whose displacement to_cartesian(f_j + (0, 0)) is bit for bit
 // j's own Cartesian position (x + 0.0 == x), so one routine serves both kinds.
 constexpr int kCentreBit = 24;
+// slow schedule variables in the f64 plane, relative to dof0() + 16 (raw bits for the integers)
+enum { kSchedScoreStart = 0, kSchedStepRatio, kSchedRejections, kSchedMoves, kSchedLoopsLeft, kSchedStage };
 // decodes a candidate bit into its image offsets
 __device__ __forceinline__ void image_of_bit(int q, int &ix, int &iy) {
     const int row = (q * 37) >> 8;  // q / 7 for q < 49
@@ -48,8 +50,11 @@ __device__ __forceinline__ void image_of_bit(int q, int &ix, int &iy) {
 // and any lane can read any replica's column (cooperative tests).
 //   f64 plane : 0 a, 1 b, 2 cos, 3 sin of the cell angle, 4 cos, 5 sin of the site angle, then per
 //               symmetry image s: 6 + 4s + {0 fx, 1 fy (wrapped fractional), 2 cx, 3 cy (Cartesian)},
-//               then the six DOFs of the current (accepted) state and their upper bounds for this
-//               stage, so that the draw loop reads "the DOF the RNG picked" with one indexed load
+//               then (at dof0()) the replica's state between moves, so that the registers hold only
+//               what every draw needs: + 0..5 the six DOFs of the current (accepted) state (the draw
+//               loop reads "the DOF the RNG picked" with one indexed load), + 6..11 their upper
+//               bounds for this stage, + 12..15 sin, cos of the site angle and of the cell angle of
+//               that state, + 16..21 the schedule's slow variables (kSched*)
 //   f32 plane : per image s, per point p: x, y of the rotated point (relative to the image's centre);
 //               last element: the squared distance below which an image is a candidate for certain
 //   masks     : N (N - 1) / 2 pair words + 1 self word (u64); in registers for multiplicities 1, 2
@@ -60,7 +65,7 @@ struct TLayout {
     __host__ __device__ TLayout(int n_items, int n_syms)
         : n(NI > 0 ? NI : n_items), N(NS > 0 ? NS : n_syms), NP((KIND == CP_POLYGON && NI == 0) ? 2 * n : n) {}
     __host__ __device__ int dof0() const { return 6 + 4 * N; }   // element of DOF 0; upper bounds follow at + 6
-    __host__ __device__ int f64_elems() const { return 18 + 4 * N; }
+    __host__ __device__ int f64_elems() const { return 28 + 4 * N; }
     __host__ __device__ int f32_elems() const { return 2 * N * NP; }
     __host__ __device__ int pairs() const { return N * (N - 1) / 2; }
     __host__ __device__ int const_doubles() const { return n * 4 + N * 6 + 6; }
@@ -176,6 +181,8 @@ struct TCands {
     unsigned long long cur = 0;         // bits of the current word still to draw
     int phase = -1;                     // words: 0 .. P - 1 the pairs i < j, P .. P + N - 1 the self word once per shape
     int remaining = 0;
+    int tune = 0;
+    int first = -1;                     // (word << 6) | bit of the candidate to draw first; -1: none
     __device__ __forceinline__ void st(int w, unsigned long long x) {
         if constexpr (kRegs) {
             if (w == 0) r0 = x; else r1 = x;
@@ -264,6 +271,29 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
     v.f32[L.f32_elems() * 32 + threadIdx.x] = s.narrow2;
     const int PW = L.pairs();
     int count = 0;
+    // The candidate nearest to its partner is drawn first: when the proposal overlaps at all it
+    // almost always overlaps there (first hit at rank 1.1 on average instead of 2.3 for a pentagon
+    // in p2, 1.05 instead of 6.5 in p2gg), and a replica leaves the pool at its first hit.
+    // Worth its instructions where a replica has many candidates (multiplicity 4: ten on average);
+    // with two shapes per cell the plain order is as fast.
+    constexpr bool kNearestFirst = NS == 0 || NS > 2;
+    float best = 3.0e38f;
+    int first = -1;
+    auto nearest = [&](unsigned long long bits, float d0x, float d0y, int w) {
+#pragma unroll 1
+        while (bits) {
+            const int q = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            int ix, iy;
+            image_of_bit(q, ix, iy);
+            const float vy = fmaf((float)iy, s.byf, d0y), vx = fmaf((float)ix, s.af, fmaf((float)iy, s.bxf, d0x));
+            const float d2 = fmaf(vx, vx, vy * vy);
+            if (d2 < best) {
+                best = d2;
+                first = (w << 6) | q;
+            }
+        }
+    };
     // a rolled loop over the pair words: a single copy of the 48-offset sweep in the kernel
 #pragma unroll 1
     for (int w = 0; w < PW; ++w) {
@@ -273,21 +303,37 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
         const unsigned long long bits = t_sweep_pair<false>(s, d0x, d0y) | (1ull << kCentreBit);
         c.st(w, bits);
         count += __popcll(bits);
+        if constexpr (kNearestFirst) nearest(bits, d0x, d0y, w);
     }
     const unsigned long long self = t_sweep_pair<true>(s, 0.0f, 0.0f);
     c.st(PW, self);
     count += __popcll(self) * L.N;
+    if constexpr (kNearestFirst) nearest(self, 0.0f, 0.0f, PW);
     c.cur = 0;
     c.phase = -1;
     c.remaining = count;
+    c.first = first;
 }
 
-// draws the next candidate of this lane (remaining > 0 guarantees there is one)
+// draws the next candidate of this lane (remaining > 0 guarantees there is one): the nearest one
+// first, then the words in order
 template <int NS>
 __device__ __forceinline__ void t_pop(TCands<NS> &c, int P, int N, int &ij, int &q) {
+    constexpr bool kNearestFirst = NS == 0 || NS > 2;
+    if (kNearestFirst && c.first >= 0 && c.phase < 0) {
+        const int w = c.first >> 6;
+        q = c.first & 63;
+        ij = w < P ? pair_of_word(w, N) : 0;  // a self image: the one of shape 0
+        c.phase = 0;
+        c.cur = c.ld(0);
+        if (w == 0) c.cur &= ~(1ull << q);
+        return;
+    }
     while (c.cur == 0ull) {
         ++c.phase;
-        c.cur = c.ld(c.phase < P ? c.phase : P);
+        const int w = c.phase < P ? c.phase : P;
+        c.cur = c.ld(w);
+        if (kNearestFirst && c.first >= 0 && c.phase == (c.first >> 6)) c.cur &= ~(1ull << (c.first & 63));
     }
     q = __ffsll((long long)c.cur) - 1;
     c.cur &= c.cur - 1;
@@ -411,10 +457,15 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
     for (;;) {
         const unsigned wanting = __ballot_sync(0xffffffffu, c.remaining > 0);
         if (wanting == 0u) break;
-        // 32 / (lanes wanting), >= 1: the pool never exceeds 32 entries (the quotient of floats is exact
-        // where it is an integer and at least 1/32 away from one otherwise)
-        const int quota = (int)__fdividef(32.0f, (float)__popc(wanting));
-        const int take = c.remaining < quota ? c.remaining : quota;
+        // every wanting lane contributes 32 / (lanes wanting) candidates, the first 32 mod (lanes wanting)
+        // of them one more: the pool holds at most 32 entries and is full whenever the lanes have
+        // that many left (the quotient of floats is exact where it is an integer and at least 1/32
+        // away from one otherwise)
+        const int nw = __popc(wanting);
+        const int quota = (int)(__fdividef(32.0f, (float)nw) + 0.01f);
+        const int rank = __popc(wanting & ((1u << lane) - 1u));
+        const int share = quota + (rank < 32 - quota * nw ? 1 : 0);
+        const int take = c.remaining < share ? c.remaining : share;
         int incl = take;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -566,11 +617,11 @@ constexpr int thread_min_blocks(int kind, int ni) {
 }
 // proposals a lane may draw per pass before the warp goes on to score what it has: the draw loop
 // is divergent (lanes leave it as they find a proposal worth scoring), so its tail is cut
-constexpr int kDrawCap = 4;  // default; KParams::draw_cap
+constexpr int kDrawCap = 3;  // default; KParams::draw_cap
 
 template <int KIND, int NI, int NS, int RNG>
 __global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI))
-mc_thread_kernel(const __grid_constant__ KParams K) {
+mc_thread_lj_kernel(const __grid_constant__ KParams K) {
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
     TView v{};
@@ -604,6 +655,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     CellCache cc = cell_cache_of(d);
     TCands<NS> cands;
     if constexpr (KIND != CP_LJ) cands.sh = v.masks + threadIdx.x;
+    cands.tune = K.tune;
     // Every lane walks its own (stage, outer loop, inner step) schedule: replicas of one warp need
     // different numbers of scored proposals per inner loop (the in-bounds fraction depends on the
     // replica's cell), and synchronising at loop ends would leave the faster lanes idle there.  Only
@@ -730,11 +782,21 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
                             // sine: the area shrinks by a relative 2e-6 or more, so new > old and the
                             // move is accepted whatever the temperature (the exact sine and score are
                             // taken in phase A); or it grows that much while kT is +0 (stages 1 and
-                            // 3), where exp(-inf) = 0 rejects.  Everything else takes the exact path.
+                            // 3), where exp(-inf) = 0 rejects, or while kT is so small that the exponent
+                            // underflows.  Everything else takes the exact path.
                             const float s_old = (float)t.sa, s_new = __sinf((float)new_val);
                             if (s_new < s_old * (1.0f - 4.0e-6f)) {
                                 settled = true;
                             } else if (s_new > s_old * (1.0f + 4.0e-6f) && __double_as_longlong(kt) == 0ll) {
+                                settled = true;
+                                have = false;
+                            } else if (s_new > s_old * (1.0f + 4.0e-6f) && kt > 0.0 &&
+                                       (float)score_current * ((s_new - s_old) / s_new - 2.0e-6f) >
+                                           746.75f * (float)kt) {
+                                // new / old = sin(old) / sin(new) exactly as real numbers, so the score falls by
+                                // at least old * rel with rel = (s_new - s_old) / s_new - 2e-6 (the f32 sines
+                                // are within 6e-7 of the exact ones).  When that is more than 746.75 kT the
+                                // exponent is below -745.14, where cp_exp returns 0: rejected.
                                 settled = true;
                                 have = false;
                             } else {
@@ -824,6 +886,285 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
         r.score = score_current;
         r.rejections = rejections;
         r.moves = moves;
+        K.out[rep] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------- hard shapes
+// Registers of the hard-shape kernel between moves: what every draw needs.  Everything else lives in
+// the lane's column of the f64 plane (TLayout) and is touched at inner-loop ends only.
+struct THot {
+    double score_current, kt, step_scale;
+    unsigned long long left;             // trial moves left in this inner loop
+    unsigned long long loop_rejections;  // optimisation.rs:100,122,134
+    Rng rng;
+    bool done;
+};
+
+// End of an inner loop (optimisation.rs:138-167), and the start of the next stage when the loop was
+// the stage's last or the stage converged (analyse_state, main.rs:224-252).  Runs once per
+// inner_steps trial moves, so it is kept out of line and works on the plane.
+template <int RNG>
+__device__ __noinline__ void t_loop_end(const KParams &K, double *mine, int e_dof, unsigned long long replica,
+                                        int n_basis, THot &h) {
+    double *sch = mine + (e_dof + 16) * 32;
+    int packed = (int)__double_as_longlong(sch[kSchedStage * 32]);
+    int stage = (packed & 0xff) - 1, convergence_count = packed >> 8;  // low byte: stage + 1 (0: none opened yet)
+    unsigned long long loops_left = (unsigned long long)__double_as_longlong(sch[kSchedLoopsLeft * 32]);
+    if (stage >= 0 && stage < K.n_stages && loops_left > 0) {  // not the call that opens the first stage
+        const KStage &S = K.stages[stage];
+        sch[kSchedMoves * 32] = __longlong_as_double(__double_as_longlong(sch[kSchedMoves * 32]) + (long long)S.inner);
+        sch[kSchedRejections * 32] =
+            __longlong_as_double(__double_as_longlong(sch[kSchedRejections * 32]) + (long long)h.loop_rejections);
+        h.kt *= S.kt_ratio;
+        bool converged = false;
+        if (S.convergence == S.convergence) {
+            if (h.score_current - sch[kSchedScoreStart * 32] < S.convergence) {
+                if (++convergence_count > 5) converged = true;
+            } else {
+                convergence_count = 0;
+            }
+        }
+        double step_ratio = sch[kSchedStepRatio * 32];
+        if (!converged && step_ratio > 1e-4) step_ratio *= (double)S.inner / ((double)h.loop_rejections + 1.);
+        sch[kSchedStepRatio * 32] = step_ratio;
+        h.step_scale = S.max_step * step_ratio;
+        --loops_left;
+        h.left = S.inner;
+        h.loop_rejections = 0;
+        sch[kSchedScoreStart * 32] = h.score_current;
+        if (converged) loops_left = 0;
+    }
+    while (loops_left == 0) {  // next stage; stages that run no move are skipped
+        ++stage;
+        if (stage >= K.n_stages) {
+            h.done = true;
+            break;
+        }
+        const KStage &S = K.stages[stage];
+        // generate_basis(): bounds captured per optimise_state call (cell.rs:139-152)
+        mine[(e_dof + 6 + 0) * 32] = mine[(e_dof + 0) * 32];
+        mine[(e_dof + 6 + 1) * 32] = mine[(e_dof + 1) * 32];
+        rng_begin_stage<RNG>(h.rng, K.seed_base, replica, n_basis);
+        h.kt = S.kt_start;
+        sch[kSchedStepRatio * 32] = 1.0;
+        h.step_scale = S.max_step * 1.0;
+        convergence_count = 0;
+        h.left = S.inner;
+        loops_left = S.inner ? S.steps / S.inner : 0ull;
+        h.loop_rejections = 0;
+        sch[kSchedScoreStart * 32] = h.score_current;
+    }
+    sch[kSchedLoopsLeft * 32] = __longlong_as_double((long long)loops_left);
+    sch[kSchedStage * 32] = __longlong_as_double((long long)((stage + 1) | (convergence_count << 8)));
+}
+
+// Monte-Carlo optimisation of hard shapes, one replica per thread (see the header comment for the
+// control flow): MCOptimiser::optimise_state (optimisation.rs:80-180) for every stage, seeds and
+// bounds per stage as analyse_state / generate_basis set them.
+// Register budget = minimum resident blocks per SM: 14 warps per SM hold all 2,048 warps of a
+// 65,536-replica batch at once.
+template <int KIND, int NI, int NS, int RNG>
+__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI))
+mc_thread_kernel(const __grid_constant__ KParams K) {
+    static_assert(KIND != CP_LJ, "hard shapes");
+    extern __shared__ double smem[];
+    const KProblem &P = K.prob;
+    const TView v = thread_view<KIND, NI, NS>(smem, P);
+    thread_stage_constants<KIND, NI, NS>(v, P);
+    const int e_dof = TLayout<KIND, NI, NS>(P.n_items, P.n_syms).dof0();
+    double *const mine = v.f64 + threadIdx.x;  // this lane's column of the f64 plane
+    const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
+    const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
+    const unsigned long long replica = K.replica_begin + (active ? rep : 0ull);
+    const int n_cell = n_cell_dof(P.family);
+    const int n_basis = n_cell + 3;
+    const double area_n = P.area * (double)P.n_syms;  // numerator of packed.rs:84
+
+    // the replica's state between moves, in the plane
+#pragma unroll
+    for (int i = 0; i < CP_MAX_DOF; ++i)
+        mine[(e_dof + i) * 32] = (K.init_dof && active) ? K.init_dof[rep * CP_MAX_DOF + i] : P.dof[i];
+    mine[(e_dof + 6 + 2) * 32] = CP_PI / 2.;  // the upper bounds that do not depend on the stage
+    mine[(e_dof + 6 + 3) * 32] = 0.5;
+    mine[(e_dof + 6 + 4) * 32] = 0.5;
+    mine[(e_dof + 6 + 5) * 32] = CP_TAU;
+    {
+        const SinCos th = dev_sincos(mine[(e_dof + 5) * 32]), an = dev_sincos(mine[(e_dof + 2) * 32]);
+        mine[(e_dof + 12) * 32] = th.s;
+        mine[(e_dof + 13) * 32] = th.c;
+        mine[(e_dof + 14) * 32] = an.s;
+        mine[(e_dof + 15) * 32] = an.c;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) mine[(e_dof + 16 + i) * 32] = 0.;  // counters 0, no stage opened yet
+
+    THot h;
+    h.score_current = 0.;
+    h.kt = 0.;
+    h.step_scale = 0.;
+    h.left = 0;
+    h.loop_rejections = 0;
+    h.done = !active;
+    TCands<NS> cands;
+    cands.sh = v.masks + threadIdx.x;
+    cands.tune = K.tune;
+    // Every lane walks its own (stage, outer loop, inner step) schedule: replicas of one warp need
+    // different numbers of scored proposals per inner loop, and synchronising at loop ends would
+    // leave the faster lanes idle there.  Only the score phases below are warp-wide.
+    // The first pass scores the initial state through the same code as every proposal
+    // (optimisation.rs:81-84: an invalid initial state is an error); `first` is warp-uniform.
+    bool first = true;
+    for (;;) {
+        bool have = false;
+        int slot = 6;  // 6 = no DOF changes (the first pass)
+        double new_val = 0., new_score = 0.;
+        unsigned long long threshold = 0ull;  // raw bits of draw #3
+        if (first) {
+            have = true;  // tail lanes score the template state too: their result is never written
+        } else {
+            // Draw until a proposal needs scoring, at most K.draw_cap draws per pass.  Out-of-bounds
+            // proposals are rejected by Basis::set_value without a score (optimisation.rs:120-123).
+            // The packing fraction depends on the cell DOFs only, so `Some(new_score)` is known
+            // before any overlap test: when the Metropolis rule would reject even a valid state (a
+            // cell move that lowers the score, lost against the threshold) the reference's answer is
+            // "rejected" whether check_intersection says None or Some, and the overlap test is
+            // skipped.  Draw order (index, step, threshold) and every decision are unchanged.
+            for (int draws = 0; draws < K.draw_cap && !h.done && !have; ++draws) {
+                if (h.left == 0) {
+                    THot at_loop_end = h;  // a copy, so that `h` itself never leaves the registers
+                    t_loop_end<RNG>(K, mine, e_dof, replica, n_basis, at_loop_end);
+                    h = at_loop_end;
+                    continue;
+                }
+                --h.left;
+                int basis_index;
+                double sample;
+                rng_draw_move<RNG>(h.rng, basis_index, sample);
+                slot = basis_to_slot(basis_index, n_cell);
+                const double val = mine[(e_dof + slot) * 32];
+                const double hi = mine[(e_dof + 6 + slot) * 32], lo = v.c_lo[slot];
+                new_val = val + h.step_scale * sample;
+                have = lo <= new_val && new_val <= hi;
+                if (!have) {
+                    ++h.loop_rejections;
+                    continue;
+                }
+                threshold = rng_draw_threshold_bits<RNG>(h.rng);
+                new_score = h.score_current;  // site moves leave the packing fraction as it is
+                if (slot <= 2) {
+                    double sa_new = mine[(e_dof + 14) * 32];
+                    bool settled = false;
+                    if (slot == 2) {
+                        // Cell-angle move.  A single-precision sine (absolute error < 2^-21 on this
+                        // range; margin 4e-6) settles the common outcomes without the f64 sine: the
+                        // area shrinks by a relative 2e-6 or more, so new > old and the move is
+                        // accepted whatever the temperature (the exact sine and score are taken in
+                        // phase A); or it grows that much while kT is +0 (stages 1 and 3), where
+                        // exp(-inf) = 0 rejects, or while kT is so small that the exponent
+                        // underflows.  Everything else takes the exact path.
+                        const float s_old = (float)sa_new, s_new = __sinf((float)new_val);
+                        if (s_new < s_old * (1.0f - 4.0e-6f)) {
+                            settled = true;
+                        } else if (s_new > s_old * (1.0f + 4.0e-6f) && __double_as_longlong(h.kt) == 0ll) {
+                            settled = true;
+                            have = false;
+                        } else if (s_new > s_old * (1.0f + 4.0e-6f) && h.kt > 0.0 &&
+                                   (float)h.score_current * ((s_new - s_old) / s_new - 2.0e-6f) > 746.75f * (float)h.kt) {
+                            // new / old = sin(old) / sin(new) exactly as real numbers, so the score falls by
+                            // at least old * rel with rel = (s_new - s_old) / s_new - 2e-6 (the f32 sines
+                            // are within 6e-7 of the exact ones).  When that is more than 746.75 kT the
+                            // exponent is below -745.14, where cp_exp returns 0: rejected.
+                            settled = true;
+                            have = false;
+                        } else {
+                            sa_new = dev_sincos(new_val).s;
+                        }
+                    }
+                    if (!settled) {
+                        const double d0 = mine[(e_dof + 0) * 32], d1 = mine[(e_dof + 1) * 32];
+                        const double len = slot == 0 ? new_val : d0, ratio = slot == 1 ? new_val : d1;
+                        const double cell_area = sa_new * len * (len * ratio);  // cell.rs:190-192
+                        new_score = area_n / cell_area;                         // packed.rs:84
+                        have = accept_move_fast(new_score, h.score_current, h.kt, threshold);
+                    }
+                    if (!have) ++h.loop_rejections;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (__all_sync(0xffffffffu, h.done)) break;
+            continue;  // every lane used up its draws without a proposal to score
+        }
+        // phase A (lanes holding a proposal): the proposed state, its geometry and its candidates
+        cands.remaining = 0;
+        double new_s = 0., new_c = 0.;
+        if (have) {
+            Dof d;
+#pragma unroll
+            for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = mine[(e_dof + i) * 32];
+            d.set(slot, new_val);
+            Trig t;
+            t.st = mine[(e_dof + 12) * 32];
+            t.ct = mine[(e_dof + 13) * 32];
+            t.sa = mine[(e_dof + 14) * 32];
+            t.ca = mine[(e_dof + 15) * 32];
+            if (slot == 2 || slot == 5) {  // the cell angle and the site angle are the only DOFs inside sin/cos
+                const SinCos sc = dev_sincos(new_val);
+                new_s = sc.s;
+                new_c = sc.c;
+                if (slot == 5) {
+                    t.st = sc.s;
+                    t.ct = sc.c;
+                } else {
+                    t.sa = sc.s;
+                    t.ca = sc.c;
+                    new_score = area_n / (t.sa * d.v[0] * (d.v[0] * d.v[1]));  // cell.rs:190-192, packed.rs:84
+                }
+            }
+            if (first) new_score = area_n / (t.sa * d.v[0] * (d.v[0] * d.v[1]));
+            t_place<KIND, NI, NS>(P, v, d, t);
+            t_sweep<KIND, NI, NS>(P, v, d, t, cell_cache_of(d), cands);
+        }
+        // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
+        const bool overlap = t_overlap_warp<KIND, NI, NS>(P, v, cands);
+        // phase C: the decision (the Metropolis rule itself was evaluated before the overlap test)
+        if (first) {
+            h.score_current = overlap ? __longlong_as_double(0x7FF8000000000000ll) : new_score;
+            if (overlap) {
+                if (active) atomicExch(K.error_flag, 1);
+                h.done = true;
+            }
+            if (!h.done) {  // opens the first stage
+                THot at_loop_end = h;
+                t_loop_end<RNG>(K, mine, e_dof, replica, n_basis, at_loop_end);
+                h = at_loop_end;
+            }
+            first = false;
+        } else if (have) {
+            if (!overlap) {
+                h.score_current = new_score;
+                mine[(e_dof + slot) * 32] = new_val;
+                if (slot == 5) {
+                    mine[(e_dof + 12) * 32] = new_s;
+                    mine[(e_dof + 13) * 32] = new_c;
+                }
+                if (slot == 2) {
+                    mine[(e_dof + 14) * 32] = new_s;
+                    mine[(e_dof + 15) * 32] = new_c;
+                }
+            } else {
+                ++h.loop_rejections;
+            }
+        }
+    }
+    if (active) {
+        cp_replica_result r;
+#pragma unroll
+        for (int i = 0; i < CP_MAX_DOF; ++i) r.dof[i] = mine[(e_dof + i) * 32];
+        r.score = h.score_current;
+        r.rejections = (unsigned long long)__double_as_longlong(mine[(e_dof + 16 + kSchedRejections) * 32]);
+        r.moves = (unsigned long long)__double_as_longlong(mine[(e_dof + 16 + kSchedMoves) * 32]);
         K.out[rep] = r;
     }
 }

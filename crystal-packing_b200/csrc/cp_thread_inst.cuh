@@ -7,9 +7,15 @@ template <int KIND, int NI, int NS, int RNG>
 static cudaError_t thread_mc_launch(const KParams &K, cudaStream_t st) {
     const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(K.prob.n_items, K.prob.n_syms);
     const unsigned grid = (unsigned)((K.n_replicas + kThreadBlock - 1) / kThreadBlock);
-    cudaError_t e = cp_allow_shared(mc_thread_kernel<KIND, NI, NS, RNG>, bytes);
-    if (e != cudaSuccess) return e;
-    mc_thread_kernel<KIND, NI, NS, RNG><<<grid, kThreadBlock, bytes, st>>>(K);
+    if constexpr (KIND == CP_LJ) {
+        cudaError_t e = cp_allow_shared(mc_thread_lj_kernel<KIND, NI, NS, RNG>, bytes);
+        if (e != cudaSuccess) return e;
+        mc_thread_lj_kernel<KIND, NI, NS, RNG><<<grid, kThreadBlock, bytes, st>>>(K);
+    } else {
+        cudaError_t e = cp_allow_shared(mc_thread_kernel<KIND, NI, NS, RNG>, bytes);
+        if (e != cudaSuccess) return e;
+        mc_thread_kernel<KIND, NI, NS, RNG><<<grid, kThreadBlock, bytes, st>>>(K);
+    }
     return cudaGetLastError();
 }
 

@@ -280,10 +280,29 @@ class Engine:
     def timing_kernel_ms(self):
         return self.timing().kernel_ms
 
-    def replay(self, problem, init_dofs, moves):
-        """moves: per replica a list of (basis_index, new_value, threshold, kt)."""
+    def images(self, problem, dofs):
+        """Per state and symmetry image: (fx, fy, cx, cy, m00, m01, m10, m11) — OccupiedSite::positions
+        and Cell2::to_cartesian_isometry as the kernels evaluate them."""
+        n, ns = len(dofs), problem.n_syms
+        flat = (C.c_double * (6 * n))(*[v for d in dofs for v in d])
+        out = (C.c_double * (8 * ns * n))()
+        _check(self._lib.cp_images(self._ctx, C.byref(problem), flat, n, out))
+        return [[tuple(out[(r * ns + s) * 8:(r * ns + s) * 8 + 8]) for s in range(ns)] for r in range(n)]
+
+    def replay(self, problem, init_dofs, moves, bound_dofs=None):
+        """moves: per replica a list of (basis_index, new_value, threshold, kt).  bound_dofs: the
+        states the bounds were captured from (default: init_dofs)."""
         n, m = len(init_dofs), len(moves[0])
         flat = (C.c_double * (6 * n))(*[v for d in init_dofs for v in d])
+        if bound_dofs is not None:
+            bflat = (C.c_double * (6 * n))(*[v for d in bound_dofs for v in d])
+            mv = (capi.Move * (n * m))()
+            for r, seq in enumerate(moves):
+                for k, (bi, nv, th, kt) in enumerate(seq):
+                    mv[r * m + k] = capi.Move(bi, 0, nv, th, kt)
+            out = (capi.Decision * (n * m))()
+            _check(self._lib.cp_replay_bounded(self._ctx, C.byref(problem), flat, bflat, mv, m, n, out))
+            return [[out[r * m + k] for k in range(m)] for r in range(n)]
         mv = (capi.Move * (n * m))()
         for r, seq in enumerate(moves):
             for k, (bi, nv, th, kt) in enumerate(seq):

@@ -123,6 +123,8 @@ SIGNATURES = {
     "cp_measure_peaks": (_i, [_ctx, _P(_d), _P(_d)]),
     "cp_score": (_i, [_ctx, _P(Problem), _P(_d), _u64, _P(_d)]),
     "cp_replay": (_i, [_ctx, _P(Problem), _P(_d), _P(Move), _u64, _u64, _P(Decision)]),
+    "cp_replay_bounded": (_i, [_ctx, _P(Problem), _P(_d), _P(_d), _P(Move), _u64, _u64, _P(Decision)]),
+    "cp_images": (_i, [_ctx, _P(Problem), _P(_d), _u64, _P(_d)]),
 }
 
 

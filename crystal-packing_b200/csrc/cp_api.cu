@@ -496,8 +496,34 @@ cp_status cp_score(cp_ctx *ctx, const cp_problem *problem, const double *dof, ui
     return CP_OK;
 }
 
+cp_status cp_images(cp_ctx *ctx, const cp_problem *problem, const double *dof, uint64_t n, double *out) {
+    if (!ctx || !dof || !out) return cp_fail(CP_ERR_INVALID_ARG, "cp_images: null argument");
+    if (n == 0) return CP_OK;
+    KProblem kp;
+    cp_status st = make_kproblem(problem, &kp);
+    if (st != CP_OK) return st;
+    CP_CUDA(cudaSetDevice(ctx->device));
+    const size_t out_bytes = sizeof(double) * 8 * kp.n_syms * n;
+    double *d_dof = nullptr, *d_out = nullptr;
+    CP_CUDA(cudaMalloc(&d_dof, sizeof(double) * CP_MAX_DOF * n));
+    cudaError_t e = cudaMalloc(&d_out, out_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_dof, dof, sizeof(double) * CP_MAX_DOF * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cp_launch_images(kp, d_dof, n, d_out, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_dof);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "cp_images");
+    return CP_OK;
+}
+
 cp_status cp_replay(cp_ctx *ctx, const cp_problem *problem, const double *init_dof, const cp_move *moves,
                     uint64_t n_moves, uint64_t n_replicas, cp_decision *out) {
+    return cp_replay_bounded(ctx, problem, init_dof, nullptr, moves, n_moves, n_replicas, out);
+}
+
+cp_status cp_replay_bounded(cp_ctx *ctx, const cp_problem *problem, const double *init_dof, const double *bound_dof,
+                            const cp_move *moves, uint64_t n_moves, uint64_t n_replicas, cp_decision *out) {
     if (!ctx || !init_dof || !moves || !out) return cp_fail(CP_ERR_INVALID_ARG, "cp_replay: null argument");
     if (n_moves == 0 || n_replicas == 0) return CP_OK;
     KProblem kp;
@@ -508,10 +534,14 @@ cp_status cp_replay(cp_ctx *ctx, const cp_problem *problem, const double *init_d
     double *d_init = nullptr;
     cp_move *d_mv = nullptr;
     cp_decision *d_out = nullptr;
-    cudaError_t e = cudaMalloc(&d_init, sizeof(double) * CP_MAX_DOF * n_replicas);
+    kp.replay_has_bounds = bound_dof ? 1 : 0;
+    const size_t dof_bytes = sizeof(double) * CP_MAX_DOF * n_replicas;
+    cudaError_t e = cudaMalloc(&d_init, dof_bytes * (bound_dof ? 2 : 1));
     if (e == cudaSuccess) e = cudaMalloc(&d_mv, sizeof(cp_move) * total);
     if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(cp_decision) * total);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_init, init_dof, sizeof(double) * CP_MAX_DOF * n_replicas, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_init, init_dof, dof_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && bound_dof)
+        e = cudaMemcpyAsync(d_init + CP_MAX_DOF * n_replicas, bound_dof, dof_bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_mv, moves, sizeof(cp_move) * total, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         const int lanes = effective_lanes(ctx, kp);

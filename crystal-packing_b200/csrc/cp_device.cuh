@@ -40,6 +40,8 @@ struct KProblem {
     float discrf[CP_MAX_ITEMS];         // disc radii
     float radf;                         // enclosing radius
     int chain;                          // polygon whose segment k ends where segment k + 1 starts
+    int replay_has_bounds;              // replay kernels: a second n x 6 block after init_dof holds the DOFs
+                                        // generate_basis captured its bounds from (cp_replay_bounded)
 };
 
 struct KStage {

@@ -204,7 +204,8 @@ replay_kernel(const __grid_constant__ KProblem P, const double *init_dof, const 
 #pragma unroll
     for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = init_dof[rep * CP_MAX_DOF + i];
     const int n_cell = n_cell_dof(P.family);
-    const double len0 = d.v[0], ratio0 = d.v[1];
+    const double *bd = P.replay_has_bounds ? init_dof + n * CP_MAX_DOF : init_dof;
+    const double len0 = bd[rep * CP_MAX_DOF + 0], ratio0 = bd[rep * CP_MAX_DOF + 1];
     double score_current = state_score<KIND, L>(P, s_items, s_shift, g, d, trig_of(d), gmask, lane);
     for (unsigned long long m = 0; m < n_moves; ++m) {
         const cp_move M = mv[rep * n_moves + m];

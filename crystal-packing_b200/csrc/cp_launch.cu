@@ -102,3 +102,8 @@ cudaError_t cp_launch_replay(const KProblem &P, int lanes, const double *init, c
     default: return cudaErrorInvalidValue;
     }
 }
+
+cudaError_t cp_launch_images(const KProblem &P, const double *dof, unsigned long long n, double *out, cudaStream_t st) {
+    images_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, dof, n, out);
+    return cudaGetLastError();
+}

@@ -13,6 +13,7 @@ cudaError_t cp_launch_score(const KProblem &P, int lanes, const double *dof, uns
                             cudaStream_t st);
 cudaError_t cp_launch_replay(const KProblem &P, int lanes, const double *init, const cp_move *mv,
                              unsigned long long n_moves, unsigned long long n, cp_decision *out, cudaStream_t st);
+cudaError_t cp_launch_images(const KProblem &P, const double *dof, unsigned long long n, double *out, cudaStream_t st);
 // does the per-thread geometry of this problem fit the one-thread-per-replica kernels?
 bool cp_thread_kernel_fits(const KProblem &P);
 size_t cp_thread_shared_bytes(const KProblem &P);

@@ -121,6 +121,28 @@ struct TPts {
     __device__ __forceinline__ float r(int k) const { return rad[k]; }
 };
 
+// One symmetry image of the occupied site: the translation column of sym * Transform2::new(theta,
+// (x, y)) wrapped into [-0.5, 0.5) (site.rs:40-45, transform.rs:107-112) and its
+// Cartesian position (cell.rs:110-112,258-263).  a = cell length, b = a * ratio.
+__device__ __forceinline__ void image_position(const double *S, const Dof &d, const Trig &t, double a, double b,
+                                               double &fx, double &fy, double &cx, double &cy) {
+    const double tx = ((S[0] * d.v[3]) + S[1] * d.v[4]) + S[2] * 1.0;
+    const double ty = ((S[3] * d.v[3]) + S[4] * d.v[4]) + S[5] * 1.0;
+    fx = wrap_unit(tx);
+    fy = wrap_unit(ty);
+    const double yb = fy * b;
+    cx = fx * a + yb * t.ca;
+    cy = yb * t.sa;
+}
+// rotation block of the same product, rows 0-1 (nalgebra's Matrix3 product order)
+__device__ __forceinline__ void image_rotation(const double *S, double ct, double st, double &m00, double &m01,
+                                               double &m10, double &m11) {
+    m00 = ((S[0] * ct) + S[1] * st) + S[2] * 0.0;
+    m01 = ((S[0] * -st) + S[1] * ct) + S[2] * 0.0;
+    m10 = ((S[3] * ct) + S[4] * st) + S[5] * 0.0;
+    m11 = ((S[3] * -st) + S[4] * ct) + S[5] * 0.0;
+}
+
 // ---------------------------------------------------------------------------------- phase A
 // OccupiedSite::positions (site.rs:33-45) and Cell2::to_cartesian_isometry (cell.rs:110-112,258-263)
 // in f64 with the reference's expressions; the rotated shape points in f32 for the certificates.
@@ -140,16 +162,12 @@ __device__ __forceinline__ void t_place(const KProblem &P, const TView &v, const
 #pragma unroll
     for (int s = 0; s < (NS > 0 ? NS : CP_MAX_SYMS); ++s) {
         if (NS == 0 && s >= L.N) break;
-        const double *S = P.syms[s];
-        // translation column of sym * Transform2::new(theta, (x, y)) (site.rs:40-45)
-        const double tx = ((S[0] * d.v[3]) + S[1] * d.v[4]) + S[2] * 1.0;
-        const double ty = ((S[3] * d.v[3]) + S[4] * d.v[4]) + S[5] * 1.0;
-        const double fx = wrap_unit(tx), fy = wrap_unit(ty);
-        const double yb = fy * b;
+        double fx, fy, cx, cy;
+        image_position(P.syms[s], d, t, a, b, fx, fy, cx, cy);
         g[(6 + 4 * s + 0) * 32] = fx;
         g[(6 + 4 * s + 1) * 32] = fy;
-        g[(6 + 4 * s + 2) * 32] = fx * a + yb * t.ca;  // cell.rs:258-263
-        g[(6 + 4 * s + 3) * 32] = yb * t.sa;
+        g[(6 + 4 * s + 2) * 32] = cx;
+        g[(6 + 4 * s + 3) * 32] = cy;
         // rotation block of the same product, single precision (certificates only)
         const float *F = P.symsf[s];
         const float m00 = fmaf(F[0], ctf, F[1] * stf), m01 = fmaf(F[1], ctf, -(F[0] * stf));
@@ -365,10 +383,9 @@ __device__ __noinline__ bool t_exact_item(const KProblem &P, const TView &v, uns
     const double radius_sq = r2x * r2x;
     // rotation blocks of sym * Transform2::new(theta, ..), rows 0-1 (site.rs:40-45)
     const double *Si = v.c_syms + i * 6, *Sj = v.c_syms + j * 6;
-    const double i00 = ((Si[0] * ct) + Si[1] * st) + Si[2] * 0.0, i01 = ((Si[0] * -st) + Si[1] * ct) + Si[2] * 0.0;
-    const double i10 = ((Si[3] * ct) + Si[4] * st) + Si[5] * 0.0, i11 = ((Si[3] * -st) + Si[4] * ct) + Si[5] * 0.0;
-    const double j00 = ((Sj[0] * ct) + Sj[1] * st) + Sj[2] * 0.0, j01 = ((Sj[0] * -st) + Sj[1] * ct) + Sj[2] * 0.0;
-    const double j10 = ((Sj[3] * ct) + Sj[4] * st) + Sj[5] * 0.0, j11 = ((Sj[3] * -st) + Sj[4] * ct) + Sj[5] * 0.0;
+    double i00, i01, i10, i11, j00, j01, j10, j11;
+    image_rotation(Si, ct, st, i00, i01, i10, i11);
+    image_rotation(Sj, ct, st, j00, j01, j10, j11);
     const double *ik = v.c_items + k * 4, *jl = v.c_items + l * 4;
     // Transform * Point without its translation (line_shape.rs:103-108)
     const double ksx = i00 * ik[0] + i01 * ik[1], ksy = i10 * ik[0] + i11 * ik[1];
@@ -1204,7 +1221,8 @@ replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof,
     for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = active ? init_dof[rep * CP_MAX_DOF + i] : P.dof[i];
     Trig t;
     const int n_cell = n_cell_dof(P.family);
-    const double len0 = d.v[0], ratio0 = d.v[1];
+    const double *bd = P.replay_has_bounds ? init_dof + n * CP_MAX_DOF : init_dof;
+    const double len0 = active ? bd[rep * CP_MAX_DOF + 0] : d.v[0], ratio0 = active ? bd[rep * CP_MAX_DOF + 1] : d.v[1];
     cp_sincos(d.v[5], &t.st, &t.ct);
     cp_sincos(d.v[2], &t.sa, &t.ca);
     double score_current = t_state_score<KIND, NI, NS>(P, v, smem, d, t, active);
@@ -1241,6 +1259,25 @@ replay_thread_kernel(const __grid_constant__ KProblem P, const double *init_dof,
         }
         D.score_current = score_current;
         if (active) out[rep * n_moves + m] = D;
+    }
+}
+
+// OccupiedSite::positions + Cell2::to_cartesian_isometry for a batch of states (site.rs:33-45,
+// cell.rs:110-112): per symmetry image fx, fy (wrapped fractional position), cx, cy (Cartesian
+// position) and the rotation block m00, m01, m10, m11, from the device functions the kernels use.
+static __global__ void __launch_bounds__(128)
+images_kernel(const __grid_constant__ KProblem P, const double *dof, unsigned long long n, double *out) {
+    const unsigned long long rep = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep >= n) return;
+    Dof d;
+#pragma unroll
+    for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = dof[rep * CP_MAX_DOF + i];
+    const Trig t = trig_of(d);
+    const double a = d.v[0], b = d.v[0] * d.v[1];
+    for (int s = 0; s < P.n_syms; ++s) {
+        double *o = out + (rep * P.n_syms + s) * 8;
+        image_position(P.syms[s], d, t, a, b, o[0], o[1], o[2], o[3]);
+        image_rotation(P.syms[s], t.ct, t.st, o[4], o[5], o[6], o[7]);
     }
 }
 

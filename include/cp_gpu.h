@@ -216,6 +216,21 @@ cp_status cp_replay(cp_ctx *ctx, const cp_problem *problem, const double *init_d
                     const cp_move *moves, uint64_t n_moves, uint64_t n_replicas,
                     cp_decision *out);
 
+/* The same with the bounds taken from another state: bound_dof (n_replicas x 6, NULL = init_dof)
+ * holds the DOFs at the time generate_basis() captured the bounds, i.e. at the start of the stage
+ * the moves were dumped from (cell.rs:139-152: length and ratio are bounded by their values then).
+ * Lets a dump from the middle of a stage be replayed from the state it was taken at. */
+cp_status cp_replay_bounded(cp_ctx *ctx, const cp_problem *problem, const double *init_dof,
+                            const double *bound_dof, const cp_move *moves, uint64_t n_moves,
+                            uint64_t n_replicas, cp_decision *out);
+
+/* OccupiedSite::positions and Cell2::to_cartesian_isometry for a batch of states (site.rs:33-45,
+ * cell.rs:110-112,258-263): dof = n x 6 host doubles; out = n x n_syms x 8 host doubles, per
+ * symmetry image the wrapped fractional position (fx, fy), the Cartesian position (cx, cy) and
+ * rows 0-1 of the rotation block (m00, m01, m10, m11) of sym * Transform2::new(theta, (x, y)),
+ * computed by the device functions the Monte-Carlo kernels use. */
+cp_status cp_images(cp_ctx *ctx, const cp_problem *problem, const double *dof, uint64_t n, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,9 @@ static cp_status cuda_fail(cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
     } while (0)
 
-// .max() over replicas ordered by score (main.rs:253, packed.rs:49-68); ties keep the lowest index
+// .max() over replicas ordered by score (main.rs:253, packed.rs:49-68).  rayon's max() is
+// reduce_with(Ord::max) in index order and Ord::max returns its second argument on Equal, so of several
+// replicas with the maximal score the one with the HIGHEST index wins.
 struct BestKey {
     double score;
     unsigned long long index;
@@ -45,7 +47,7 @@ __device__ __forceinline__ bool better(const BestKey &a, const BestKey &b) {
     // is a better than b?  NaN (None) never wins
     if (!(a.score == a.score)) return false;
     if (!(b.score == b.score)) return true;
-    return a.score > b.score || (a.score == b.score && a.index < b.index);
+    return a.score > b.score || (a.score == b.score && a.index > b.index);
 }
 __global__ void __launch_bounds__(256)
 best_kernel(const cp_replica_result *res, const BestKey *partial_in, unsigned long long n, BestKey *out,

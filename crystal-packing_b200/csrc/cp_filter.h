@@ -38,10 +38,13 @@
 //
 // The f32 evaluation works in coordinates relative to A's centre: A's points a_k (|a_k| <= R), B's
 // points b_l + delta, delta = B's centre - A's centre rounded from f64.  With eps = 2^-24, points
-// carrying an absolute error <= 4 eps R (rotation evaluated in f32) and V = 2R + |delta|, every H
-// and G is within E = 24 eps R (R + V) of its real value (edge vector 10 eps R x |w|, w 10 eps R +
-// 2 eps V x |d| <= 2R, three roundings of the cross product).  tau = 2^-16 R (3R + |dx| + |dy|)
-// >= 256 eps R (R + V) leaves a factor ten.
+// carrying an absolute error <= 8 eps R (rotation evaluated in f32 from the f32 sine and cosine) and
+// |delta| <= |dx| + |dy|: an edge vector (difference of two unshifted points) is within 18 eps R,
+// a shifted point within 9 eps R + 2 eps |delta|, and the three roundings of a cross product add
+// 8 eps R (2R + |delta|); every H and G is therefore within E = 30 eps R (3R + |delta|) of its real
+// value.  tau = 2^-18 R (3R + |dx| + |dy|) = 64 eps R (3R + |delta|_1) leaves a factor two on top of
+// these (generous) bounds; tests/filter_check.cpp checks the certificates against the f64
+// evaluation along real trajectories.
 //
 // Mirror images.  The reference tests shape i against image t of shape j AND shape j against image
 // -t of shape i: the same configuration translated by -t, with the roles of the two shapes (and so
@@ -50,8 +53,9 @@
 // (< 1e-14 R), so one certificate covers both.  The caller enumerates half of the ordered pairs.
 //
 // ---- discs ---------------------------------------------------------------------------------------
-// Atom2::intersects is  dx*dx + dy*dy < (r1 + r2)^2.  s = (r1 + r2)^2 - |d|^2 in f32 is within
-// 8 eps (R + V)^2 of the real value, the f64 evaluation within 1e-15 (R + V)^2; cmin = -max s.
+// Atom2::intersects is  dx*dx + dy*dy < (r1 + r2)^2.  c = |d|^2 - (r1 + r2)^2 in f32 is within
+// 30 eps (3R + |delta|)^2 of the real value, the f64 evaluation within 1e-15 of it; tau =
+// 2^-18 (3R + |delta|_1)^2; cmin = min c.
 #ifndef CP_FILTER_H
 #define CP_FILTER_H
 
@@ -203,6 +207,65 @@ CPF_HD float cpf_discs(int n_rt, const PtsA &A, const PtsB &B, float dX, float d
 CPF_HD float cpf_tau_discs(float R, float dx, float dy) {
     const float w = fmaf(3.0f, R, fabsf(dx) + fabsf(dy));
     return 3.814697265625e-06f * w * w;
+}
+
+// ---- the image sweep -----------------------------------------------------------------------------
+// PackedState::check_intersection keeps an image (ix, iy) of a shape when dx*dx + dy*dy <= (2R)^2 in
+// f64 (packed.rs:150-157).  Here the displacement of the image is d0 + ix a + iy b from f32 copies of
+// the lattice vectors a = (af, 0), b = (bxf, byf); its error is below 2^-24 (|d0|_1 + 6 (|a| + |b|)),
+// so with delta = 2^-19 (|a| + |b|) / R + 2^-20 every image the reference keeps has
+// d2 <= (2R)^2 (1 + delta) here: those are the candidates.  Whether a candidate is one the
+// reference keeps FOR CERTAIN is decided where its certificate is evaluated, from the f64
+// displacement rounded to f32, against narrow2 = (2R)^2 (1 - delta).
+// Bit (iy + 3) * 7 + (ix + 3) of the result stands for image (ix, iy), |ix|, |iy| <= shells <= 3.
+// All 48 offsets of three shells are evaluated in straight-line code (four instructions each, no
+// branches): in the packings the optimiser converges to, the cells are skewed enough that
+// periodic_range is 3 for nine moves out of ten (packed.rs:128-132), and loops over the few offsets
+// in reach cost more in branch latency than they save.
+// SELF: the images of a shape against itself come in mirror pairs t, -t; only iy > 0, and ix > 0 on
+// the row iy = 0, are produced.
+struct CpfSweep {
+    float af, bxf, byf;
+    float wide2, narrow2;
+    int shells;
+};
+CPF_HD CpfSweep cpf_sweep_setup(float af, float bxf, float byf, float R, int shells) {
+    CpfSweep s;
+    s.af = af;
+    s.bxf = bxf;
+    s.byf = byf;
+    const float r2x = 2.0f * R;
+    const float delta = fmaf(1.9073486328125e-06f, (af + fabsf(bxf) + fabsf(byf)) / R, 9.5367431640625e-07f);
+    s.wide2 = r2x * r2x * (1.0f + delta);
+    s.narrow2 = r2x * r2x * (1.0f - delta);
+    s.shells = shells;
+    return s;
+}
+template <bool SELF>
+CPF_HD unsigned long long cpf_sweep_pair(const CpfSweep &s, float d0x, float d0y) {
+    const bool ring2 = s.shells >= 2, ring3 = s.shells >= 3;
+    unsigned lo = 0u, hi = 0u;
+#pragma unroll
+    for (int iy = SELF ? 0 : -3; iy <= 3; ++iy) {
+        const float vy = fmaf((float)iy, s.byf, d0y), x0 = fmaf((float)iy, s.bxf, d0x);
+        const float vy2 = vy * vy;
+        unsigned row = 0u;
+#pragma unroll
+        for (int ix = (SELF && iy == 0) ? 1 : -3; ix <= 3; ++ix) {
+            if (ix == 0 && iy == 0) continue;  // the zero offset is not an image (cell.rs:216-225)
+            const int ring = (ix < 0 ? -ix : ix) > (iy < 0 ? -iy : iy) ? (ix < 0 ? -ix : ix) : (iy < 0 ? -iy : iy);
+            const float vx = fmaf((float)ix, s.af, x0);
+            const float d2 = fmaf(vx, vx, vy2);
+            bool in = d2 <= s.wide2;
+            if (ring == 2) in = in && ring2;
+            if (ring == 3) in = in && ring3;
+            row |= in ? 1u << (ix + 3) : 0u;
+        }
+        const int sh = (iy + 3) * 7;  // row iy occupies bits sh .. sh + 6
+        if (sh < 32) lo |= row << sh;
+        if (sh + 7 > 32) hi |= sh >= 32 ? row << (sh - 32) : row >> (32 - sh);
+    }
+    return ((unsigned long long)hi << 32) | lo;
 }
 
 #endif  // CP_FILTER_H

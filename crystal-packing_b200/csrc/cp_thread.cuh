@@ -220,60 +220,10 @@ __device__ __forceinline__ int pair_of_word(int w, int N) {
     return (int)((lut >> (4 * w)) & 15u);
 }
 
-// The image sweep in single precision.  The reference keeps an image when dx*dx + dy*dy <= (2R)^2 in
-// f64 (packed.rs:150-157).  Here the displacement of image (ix, iy) is d0 + ix a + iy b from f32
-// copies of the lattice vectors; its error is below 2^-24 (|d0|_1 + 6 (|a| + |b|)), so with
-// delta = 2^-19 (|a| + |b|) / R + 2^-20 every image the reference keeps has d2 <= (2R)^2 (1 + delta)
-// here: those are the candidates.  Whether a candidate is one the reference keeps FOR CERTAIN is
-// decided where its certificate is evaluated (t_overlap_warp), from the f64 displacement, against
-// (2R)^2 (1 - delta) kept in the f32 plane.
-// All 48 offsets of three shells are evaluated in straight-line code (four instructions each, no
-// branches): in the packings the optimiser converges to, the cells are skewed enough that
-// periodic_range is 3 for nine moves out of ten (packed.rs:128-132), and loops over the few offsets
-// in reach cost more in branch latency than they save.
-struct TSweep {
-    float af, bxf, byf;  // a = (af, 0), b = (bxf, byf)
-    float wide2, narrow2;
-    int shells;
-};
-__device__ __forceinline__ TSweep t_sweep_setup(const KProblem &P, const Dof &d, const Trig &t, const CellCache &cc) {
-    TSweep s;
+// The image sweep (cp_filter.h: cpf_sweep_setup, cpf_sweep_pair) on this lane's proposal.
+__device__ __forceinline__ CpfSweep t_sweep_setup(const KProblem &P, const Dof &d, const Trig &t, const CellCache &cc) {
     const double b = d.v[0] * d.v[1];
-    s.af = (float)d.v[0];
-    s.bxf = (float)(b * t.ca);
-    s.byf = (float)(b * t.sa);
-    const float r2x = 2.0f * P.radf;
-    const float delta = fmaf(1.9073486328125e-06f, (s.af + fabsf(s.bxf) + fabsf(s.byf)) / P.radf, 9.5367431640625e-07f);
-    s.wide2 = r2x * r2x * (1.0f + delta);
-    s.narrow2 = r2x * r2x * (1.0f - delta);
-    s.shells = cc.shells;
-    return s;
-}
-template <bool SELF>
-__device__ __forceinline__ unsigned long long t_sweep_pair(const TSweep &s, float d0x, float d0y) {
-    const bool ring2 = s.shells >= 2, ring3 = s.shells >= 3;
-    unsigned lo = 0u, hi = 0u;
-#pragma unroll
-    for (int iy = SELF ? 0 : -3; iy <= 3; ++iy) {
-        const float vy = fmaf((float)iy, s.byf, d0y), x0 = fmaf((float)iy, s.bxf, d0x);
-        const float vy2 = vy * vy;
-        unsigned row = 0u;
-#pragma unroll
-        for (int ix = (SELF && iy == 0) ? 1 : -3; ix <= 3; ++ix) {
-            if (ix == 0 && iy == 0) continue;  // the zero offset is not an image (cell.rs:216-225)
-            const int ring = (ix < 0 ? -ix : ix) > (iy < 0 ? -iy : iy) ? (ix < 0 ? -ix : ix) : (iy < 0 ? -iy : iy);
-            const float vx = fmaf((float)ix, s.af, x0);
-            const float d2 = fmaf(vx, vx, vy2);
-            bool in = d2 <= s.wide2;
-            if (ring == 2) in = in && ring2;
-            if (ring == 3) in = in && ring3;
-            row |= in ? 1u << (ix + 3) : 0u;
-        }
-        const int sh = (iy + 3) * 7;  // row iy occupies bits sh .. sh + 6
-        if (sh < 32) lo |= row << sh;
-        if (sh + 7 > 32) hi |= sh >= 32 ? row << (sh - 32) : row >> (32 - sh);
-    }
-    return ((unsigned long long)hi << 32) | lo;
+    return cpf_sweep_setup((float)d.v[0], (float)(b * t.ca), (float)(b * t.sa), P.radf, cc.shells);
 }
 
 // Candidate generation for PackedState::check_intersection (state/packed.rs:127-167), half of the
@@ -285,7 +235,7 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
                                         const CellCache &cc, TCands<NS> &c) {
     const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
     const double *g = v.f64 + threadIdx.x;
-    const TSweep s = t_sweep_setup(P, d, t, cc);
+    const CpfSweep s = t_sweep_setup(P, d, t, cc);
     v.f32[L.f32_elems() * 32 + threadIdx.x] = s.narrow2;
     const int PW = L.pairs();
     int count = 0;
@@ -318,12 +268,12 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
         const int ij = pair_of_word(w, L.N), i = ij >> 2, j = ij & 3;
         const float d0x = (float)(g[(6 + 4 * j + 2) * 32] - g[(6 + 4 * i + 2) * 32]);
         const float d0y = (float)(g[(6 + 4 * j + 3) * 32] - g[(6 + 4 * i + 3) * 32]);
-        const unsigned long long bits = t_sweep_pair<false>(s, d0x, d0y) | (1ull << kCentreBit);
+        const unsigned long long bits = cpf_sweep_pair<false>(s, d0x, d0y) | (1ull << kCentreBit);
         c.st(w, bits);
         count += __popcll(bits);
         if constexpr (kNearestFirst) nearest(bits, d0x, d0y, w);
     }
-    const unsigned long long self = t_sweep_pair<true>(s, 0.0f, 0.0f);
+    const unsigned long long self = cpf_sweep_pair<true>(s, 0.0f, 0.0f);
     c.st(PW, self);
     count += __popcll(self) * L.N;
     if constexpr (kNearestFirst) nearest(self, 0.0f, 0.0f, PW);

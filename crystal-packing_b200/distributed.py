@@ -23,6 +23,43 @@ def weak_range(per_rank, rank):
     return rank * per_rank, per_rank
 
 
+# ---------------------------------------------------------------------------------- sweeps of cells
+# BASELINE.json configs[4]: every (polygon, plane group) cell is its own batch of replicas, and a
+# replica of a 12-gon in a multiplicity-4 group costs ~18x one of a triangle in p1.  A fixed batch
+# is therefore split over the ranks by COST, not by count: the cells are cut into chunks of
+# replicas and the chunks dealt out longest-first.
+SWEEP_GROUPS = ("p1", "p2", "p1m1", "p1g1", "p2mm", "p2mg", "p2gg")
+
+
+def sweep_cells(sides=range(3, 13), groups=SWEEP_GROUPS):
+    return [(n, g) for n in sides for g in groups]
+
+
+def split_chunks(n_cells, replicas_per_cell, chunks_per_cell):
+    """(cell, replica_begin, count) pieces of every cell; seeds stay the replica's index within its
+    cell, so the results do not depend on how the cells were cut."""
+    out = []
+    for c in range(n_cells):
+        for k in range(chunks_per_cell):
+            begin, count = shard_range(replicas_per_cell, k, chunks_per_cell)
+            if count:
+                out.append((c, begin, count))
+    return out
+
+
+def lpt_assign(costs, world):
+    """Longest-processing-time-first: chunk indices per rank and the estimated load of each rank.
+    Deterministic (ties by index), so every rank computes the same assignment from the same costs."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world
+    mine = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (loads[k], k))
+        mine[r].append(i)
+        loads[r] += costs[i]
+    return mine, loads
+
+
 def pack_best(dof, score, rejections, moves, replica):
     return struct.pack(_FMT, *dof, score, rejections, moves, replica)
 
@@ -33,14 +70,16 @@ def unpack_best(buf):
 
 
 def pick_best(records):
-    """argmax by score, NaN (None) never wins, ties -> lowest replica id (rayon's max leaves tie
-    order unspecified; this makes it deterministic and independent of the sharding)."""
+    """argmax by score, NaN (None) never wins, ties -> HIGHEST replica id: rayon's max() is
+    reduce_with(Ord::max) in index order and Ord::max returns its second argument on Equal
+    (main.rs:253), so the reference keeps the last of several maximal replicas.  Independent of the
+    sharding."""
     best = None
     for r in records:
         if r["score"] != r["score"]:
             continue
         if best is None or r["score"] > best["score"] or (
-                r["score"] == best["score"] and r["replica"] < best["replica"]):
+                r["score"] == best["score"] and r["replica"] > best["replica"]):
             best = r
     return best
 

@@ -107,7 +107,8 @@ typedef struct {
 
 typedef struct {
     cp_replica_result result;
-    uint64_t replica; /* global replica index (= seed) of the best state; ties -> lowest index */
+    uint64_t replica; /* global replica index (= seed) of the best state; of several replicas with the
+                         maximal score the highest index, as rayon's max() returns (main.rs:253) */
 } cp_best;
 
 /* one replayed trial move (inputs): what optimisation.rs:104-119,62 drew for this move */

@@ -24,6 +24,15 @@
 
 /* ------------------------------------------------------------------ counters */
 static __thread orc_counters g_cnt;
+/* The operation counters feed bench.py's FLOPs-per-move figure.  The TIMED build of the oracle
+ * (libcp_oracle_fast.so: -O3 -march=native -DORC_NO_COUNTERS, see the Makefile) compiles them out:
+ * a thread-local read-modify-write inside every segment / disc / LJ test would handicap the CPU
+ * baseline against a release build of the reference, which has none. */
+#ifdef ORC_NO_COUNTERS
+#define ORC_COUNT(stmt) ((void)0)
+#else
+#define ORC_COUNT(stmt) (g_cnt.stmt)
+#endif
 
 void orc_counters_reset(void) { memset(&g_cnt, 0, sizeof g_cnt); }
 void orc_counters_get(orc_counters *out) { *out = g_cnt; }
@@ -141,7 +150,7 @@ double orc_cp_exp(double x) { return cp_exp(x); }
 
 void orc_sincos(int math_mode, double x, double *s, double *c)
 {
-    g_cnt.trig += 2;
+    ORC_COUNT(trig += 2);
     if (math_mode == ORC_MATH_CP) {
         cp_sincos(x, s, c);
     } else {
@@ -152,7 +161,7 @@ void orc_sincos(int math_mode, double x, double *s, double *c)
 
 double orc_exp(int math_mode, double x)
 {
-    g_cnt.trig += 1;
+    ORC_COUNT(trig += 1);
     return math_mode == ORC_MATH_CP ? cp_exp(x) : exp(x);
 }
 
@@ -194,7 +203,7 @@ void orc_transform_mul_point(const orc_transform *t, double px, double py, doubl
 {
     /* transform.rs:64-70 -> nalgebra Transform<TGeneral> * Point: (M2x2*p + translation), divided
      * by the normaliser n = m20*px + m21*py + m22 only when n != 0 */
-    g_cnt.point_xforms += 1;
+    ORC_COUNT(point_xforms += 1);
     double vx = (t->m[0][0] * px + t->m[0][1] * py) + t->m[0][2];
     double vy = (t->m[1][0] * px + t->m[1][1] * py) + t->m[1][2];
     double n = (t->m[2][0] * px + t->m[2][1] * py) + t->m[2][2];
@@ -210,7 +219,7 @@ void orc_transform_position(const orc_transform *t, double *ox, double *oy)
 {
     /* transform.rs:93-95: self.0 * Point2::origin() */
     orc_transform_mul_point(t, 0.0, 0.0, ox, oy);
-    g_cnt.point_xforms -= 1; /* bookkeeping: position() is a column read, not counted as work */
+    ORC_COUNT(point_xforms -= 1); /* bookkeeping: position() is a column read, not counted as work */
 }
 
 static double wrap_coord(double v, double period, double offset)
@@ -302,7 +311,7 @@ void orc_cell_to_cartesian(const orc_state *s, double x, double y, double *ox, d
      * sin of the cell angle on every call */
     double sn, cs;
     orc_sincos(s->math_mode, s->angle, &sn, &cs);
-    g_cnt.trig -= 2; /* the reference re-evaluates cos/sin per call; §8d counts the cell trig once per score */
+    ORC_COUNT(trig -= 2); /* the reference re-evaluates cos/sin per call; §8d counts the cell trig once per score */
     *ox = x * cell_a(s) + y * cell_b(s) * cs;
     *oy = y * cell_b(s) * sn;
 }
@@ -312,7 +321,7 @@ double orc_cell_area(const orc_state *s)
     /* cell.rs:190-192 */
     double sn, cs;
     orc_sincos(s->math_mode, s->angle, &sn, &cs);
-    g_cnt.trig -= 2;
+    ORC_COUNT(trig -= 2);
     return sn * cell_a(s) * cell_b(s);
 }
 
@@ -357,7 +366,7 @@ int orc_cell_periodic_images(const orc_state *s, const orc_transform *t, int she
 int orc_line_intersects(const orc_item *s, const orc_item *o)
 {
     /* line2.rs:29-54 with dx/dy from :94-101; item = (x0,y0,x1,y1) */
-    g_cnt.segment_tests += 1;
+    ORC_COUNT(segment_tests += 1);
     double s_dx = s->c - s->a, s_dy = s->d - s->b;
     double o_dx = o->c - o->a, o_dy = o->d - o->b;
     double u_b = o_dy * s_dx - o_dx * s_dy;
@@ -375,7 +384,7 @@ int orc_line_intersects(const orc_item *s, const orc_item *o)
 int orc_atom_intersects(const orc_item *s, const orc_item *o)
 {
     /* atom2.rs:21-26; item = (x, y, radius) */
-    g_cnt.disc_tests += 1;
+    ORC_COUNT(disc_tests += 1);
     double rs = s->c + o->c;
     double r_squared = rs * rs;
     double dx = s->a - o->a, dy = s->b - o->b;
@@ -407,15 +416,15 @@ double orc_lj_energy(const orc_item *s, const orc_item *o)
     if (s->e == s->e) {      /* Some(cutoff) */
         double x = s->e;
         if (r_squared < x * x) {
-            g_cnt.lj_in += 1;
+            ORC_COUNT(lj_in += 1);
             double sx = s->c / x;
             double shift = 4.0 * s->d * (powi12(sx) - powi6(s->c / x));
             return 4.0 * s->d * (c3 * c3 - c3) - shift;
         }
-        g_cnt.lj_out += 1;
+        ORC_COUNT(lj_out += 1);
         return 0.0;
     }
-    g_cnt.lj_in += 1;
+    ORC_COUNT(lj_in += 1);
     return 4.0 * s->d * (c3 * c3 - c3);
 }
 
@@ -660,7 +669,7 @@ int orc_state_relative_positions(const orc_state *s, orc_transform *out)
     orc_transform t, p;
     orc_transform_new(s->math_mode, s->theta, s->x, s->y, &t);
     for (int i = 0; i < s->n_syms; ++i) {
-        g_cnt.site_images += 1;
+        ORC_COUNT(site_images += 1);
         orc_transform_mul(&s->syms[i], &t, &p);
         orc_transform_periodic(&p, 1.0, -0.5, &out[i]);
     }
@@ -712,12 +721,12 @@ int orc_state_check_intersection(const orc_state *s)
         for (int j = 0; j < n; ++j) {
             int ni = orc_cell_periodic_images(s, &rel[j], periodic_range, 0, images);
             for (int k = 0; k < ni; ++k) {
-                g_cnt.image_cands += 1;
+                ORC_COUNT(image_cands += 1);
                 double dx = cart[i].m[0][2] - images[k].m[0][2];
                 double dy = cart[i].m[1][2] - images[k].m[1][2];
                 double distance = dx * dx + dy * dy;
                 if (distance <= radius_sq) {
-                    g_cnt.image_pass += 1;
+                    ORC_COUNT(image_pass += 1);
                     orc_shape_transform(s->kind, s->items, s->n_items, &images[k], shape2);
                     if (orc_shape_intersects(s->kind, shapes[i], shape2, s->n_items))
                         return 1;
@@ -748,7 +757,7 @@ static double potential_score(const orc_state *s)
         for (int j = 0; j < n; ++j) {
             int ni = orc_cell_periodic_images(s, &rel[j], 3, 0, images);
             for (int k = 0; k < ni; ++k) {
-                g_cnt.image_cands += 1;
+                ORC_COUNT(image_cands += 1);
                 orc_shape_transform(s->kind, s->items, s->n_items, &images[k], shape2);
                 sum += orc_shape_energy(shapes[i], shape2, s->n_items);
             }
@@ -758,8 +767,8 @@ static double potential_score(const orc_state *s)
 
 double orc_state_score(const orc_state *s)
 {
-    g_cnt.scored += 1;
-    g_cnt.trig += 2; /* cos + sin of the cell angle ("cell trig = 2") */
+    ORC_COUNT(scored += 1);
+    ORC_COUNT(trig += 2); /* cos + sin of the cell angle ("cell trig = 2") */
     if (s->kind == ORC_LJ)
         return potential_score(s);
     /* packed.rs:80-86 */
@@ -913,7 +922,7 @@ int orc_optimise_state(const orc_optimiser *opt, orc_state *s, orc_move_record *
         double score_start = score_current;
         uint64_t loop_rejections = 0;
         for (uint64_t it = 0; it < opt->inner_steps; ++it) {
-            g_cnt.moves += 1;
+            ORC_COUNT(moves += 1);
             int basis_index = (int)orc_uniform_usize(&rng, (uint64_t)n_basis);
             double *b = dof_ptr(s, basis_index);
             double val = *b;
@@ -969,7 +978,7 @@ int orc_optimise_state(const orc_optimiser *opt, orc_state *s, orc_move_record *
     {
         /* assert!(state.score().is_some()) */
         double final_score = orc_state_score(s);
-        g_cnt.scored -= 1;
+        ORC_COUNT(scored -= 1);
         if (!(final_score == final_score)) {
             if (n_records)
                 *n_records = n_moves;
@@ -1073,8 +1082,10 @@ static void *worker(void *p)
         orc_run_replica(w->tmpl, w->b, w->begin + i, NULL, &r);
         if (w->results)
             w->results[i] = r;
-        /* .max() over states ordered by score (packed.rs:49-68); ties: keep the lowest index */
-        if (r.score == r.score && (w->best_index < 0 || r.score > w->best.score)) {
+        /* .max() over states ordered by score (packed.rs:49-68).  rayon's max() is
+         * reduce_with(Ord::max) in index order and Ord::max returns its second argument when the two
+         * compare equal, so of several replicas with the maximal score the LAST one wins. */
+        if (r.score == r.score && (w->best_index < 0 || r.score >= w->best.score)) {
             w->best = r;
             w->best_index = (int64_t)i;
         }
@@ -1115,7 +1126,7 @@ int64_t orc_analyse_state_counted(const orc_state *tmpl, const orc_build_optimis
         counters_add(&total, &args[t].counters);
         if (args[t].best_index >= 0 &&
             (best_index < 0 || args[t].best.score > best_r.score ||
-             (args[t].best.score == best_r.score && args[t].best_index < best_index))) {
+             (args[t].best.score == best_r.score && args[t].best_index > best_index))) {
             best_r = args[t].best;
             best_index = args[t].best_index;
         }

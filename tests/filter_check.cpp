@@ -10,7 +10,7 @@
 //     orc_state_check_intersection.
 // Prints one JSON line with the statistics the kernel design rests on.
 //
-// usage: filter_check <kind: polygon|trimer|circle> <sides> <group> <replicas> <steps> [kt_start kt_finish]
+// usage: filter_check <polygon|star|soup|trimer|circle> <sides> <group> <replicas> <steps> [kt_start kt_finish]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -130,35 +130,70 @@ static int filtered_check(const orc_state *s, bool chain, Stats &st) {
             }
         }
     }
-    // candidate list: in-cell pairs, then images of i < j (all offsets), then the canonical half of
-    // the self images (taken from shape 0, applied to every shape)
+    // candidate list exactly as the kernel builds it (cp_thread.cuh: t_sweep): the single-precision
+    // sweep over half of the ordered pairs; `band` = the certificate's evaluation site cannot be sure
+    // the reference keeps the image (the f64 displacement, rounded, against narrow2)
     std::vector<Cand> cl;
-    for (int i = 0; i < N; ++i)
-        for (int j = i + 1; j < N; ++j) cl.push_back(Cand{i, j, 0, 0, true, false, cx[j], cy[j]});
-    const double wide = radius_sq * (1.0 + 1e-9), narrow = radius_sq * (1.0 - 1e-9);
-    for (int i = 0; i < N; ++i)
-        for (int j = i + 1; j < N; ++j)
-            for (int ix = -shells; ix <= shells; ++ix)
-                for (int iy = -shells; iy <= shells; ++iy) {
-                    if (ix == 0 && iy == 0) continue;
-                    double ffx = fx[j] + (double)ix, ffy = fy[j] + (double)iy;
-                    double yb = ffy * b, X = ffx * a + yb * ca, Y = yb * sa;
-                    double ddx = cx[i] - X, ddy = cy[i] - Y, d2 = ddx * ddx + ddy * ddy;
-                    if (d2 <= wide) cl.push_back(Cand{i, j, ix, iy, false, !(d2 <= narrow), X, Y});
-                }
-    for (int ix = -shells; ix <= shells; ++ix)
-        for (int iy = -shells; iy <= shells; ++iy) {
-            if (!(iy > 0 || (iy == 0 && ix > 0))) continue;
-            double ffx = fx[0] + (double)ix, ffy = fy[0] + (double)iy;
-            double yb = ffy * b, X = ffx * a + yb * ca, Y = yb * sa;
-            double ddx = cx[0] - X, ddy = cy[0] - Y, d2 = ddx * ddx + ddy * ddy;
-            if (d2 <= wide)
-                for (int i = 0; i < N; ++i) {
-                    double fix = fx[i] + (double)ix, fiy = fy[i] + (double)iy;
-                    double ybi = fiy * b;
-                    cl.push_back(Cand{i, i, ix, iy, false, !(d2 <= narrow), fix * a + ybi * ca, ybi * sa});
-                }
+    const CpfSweep sw = cpf_sweep_setup((float)a, (float)(b * ca), (float)(b * sa), (float)R, shells);
+    auto push_word = [&](unsigned long long bits, int i, int j) {
+        while (bits) {
+            const int q = __builtin_ctzll(bits);
+            bits &= bits - 1;
+            const int row = q / 7, iy = row - 3, ix = q - row * 7 - 3;
+            const double ffx = fx[j] + (double)ix, ffy = fy[j] + (double)iy;
+            const double yb = ffy * b, X = ffx * a + yb * ca, Y = yb * sa;
+            const bool incell = ix == 0 && iy == 0;
+            const float dX = (float)(X - cx[i]), dY = (float)(Y - cy[i]);
+            const bool band = !incell && !(fmaf(dX, dX, dY * dY) <= sw.narrow2);
+            cl.push_back(Cand{i, j, ix, iy, incell, band, X, Y});
         }
+    };
+    std::vector<unsigned long long> words;
+    for (int i = 0; i < N; ++i)
+        for (int j = i + 1; j < N; ++j) {
+            const unsigned long long bits =
+                cpf_sweep_pair<false>(sw, (float)(cx[j] - cx[i]), (float)(cy[j] - cy[i])) | (1ull << 24);
+            words.push_back(bits);
+            push_word(bits, i, j);
+        }
+    const unsigned long long self = cpf_sweep_pair<true>(sw, 0.0f, 0.0f);
+    for (int i = 0; i < N; ++i) push_word(self, i, i);
+    // the sweep must not miss anything the reference tests: every ordered pair, every image within
+    // `shells` that passes the f64 filter (packed.rs:152-157) is in the list, itself or as its mirror
+    {
+        int w = 0;
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j)
+                for (int ix = -shells; ix <= shells; ++ix)
+                    for (int iy = -shells; iy <= shells; ++iy) {
+                        if (ix == 0 && iy == 0) continue;
+                        const double ffx = fx[j] + (double)ix, ffy = fy[j] + (double)iy;
+                        const double yb = ffy * b, X = ffx * a + yb * ca, Y = yb * sa;
+                        const double ddx = cx[i] - X, ddy = cy[i] - Y;
+                        if (!(ddx * ddx + ddy * ddy <= radius_sq)) continue;
+                        bool listed;
+                        if (i < j) {
+                            int wi = 0;
+                            for (int p = 0; p < i; ++p) wi += N - 1 - p;
+                            wi += j - i - 1;
+                            listed = (words[wi] >> ((iy + 3) * 7 + (ix + 3))) & 1ull;
+                        } else if (i > j) {
+                            int wi = 0;
+                            for (int p = 0; p < j; ++p) wi += N - 1 - p;
+                            wi += i - j - 1;
+                            listed = (words[wi] >> ((-iy + 3) * 7 + (-ix + 3))) & 1ull;
+                        } else {
+                            const bool upper = iy > 0 || (iy == 0 && ix > 0);
+                            const int qx = upper ? ix : -ix, qy = upper ? iy : -iy;
+                            listed = (self >> ((qy + 3) * 7 + (qx + 3))) & 1ull;
+                        }
+                        if (!listed) {
+                            st.errors++;
+                            std::fprintf(stderr, "SWEEP MISSED a reference candidate: (%d,%d) image (%d,%d)\n", i, j, ix, iy);
+                        }
+                    }
+        (void)w;
+    }
     st.scored++;
     st.cands += cl.size();
     if (cl.size() > st.max_cands) st.max_cands = cl.size();

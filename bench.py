@@ -20,6 +20,12 @@ one exchange is the 80-byte all-gather of each rank's best state.
             achieved = reference-formula FLOPs per move (oracle counters, SURVEY.md §8d unit costs)
             x moves per launch / kernel time; peak = FP64 FMA throughput measured here
   cpu_baseline  the C restatement of the reference's rayon path on all host cores, bounded sample
+                (oracle/libcp_oracle_fast.so: -O3 -march=native, operation counters compiled out)
+  configs   the other BASELINE.json configurations, device-resident and device-timed like `value`:
+            C3 (disc trimer in p2gg with annealing, 262,144 replicas/GPU, weak), C4 (LJ trimer in
+            p2gg, 131,072 replicas/GPU = 1,048,576 on 8 GPUs, weak) and C5 (3..12-gons x 7 plane
+            groups, 8,388,590 replicas in total, STRONG: the 70 cells are cut into chunks and dealt
+            to the ranks by measured cost; per-rank kernel times are printed)
 """
 import argparse
 import ctypes
@@ -53,6 +59,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--configs", default="c3,c4,c5", help="extra BASELINE configurations to time (comma list, '' = none)")
+    ap.add_argument("--config-steps", type=int, default=2, help="timed passes of each extra configuration")
+    ap.add_argument("--c5-total", type=int, default=8388608, help="replicas of the C5 sweep (rounded down to 70 equal cells)")
+    ap.add_argument("--c5-mc-steps", type=int, default=1000)
     return ap.parse_args()
 
 
@@ -72,36 +82,49 @@ def workload_config(args, world):
         "moves_per_replica": moves_per_replica(args),
         "rng": "philox4x32-10 (production stream; PCG64-MCG replay is the parity mode)",
         "parallelism": f"replica-sharded x{world}, no data-path collective",
-        "l2": "256 MiB write between timed steps (working set is KBs; L2 state is irrelevant to an FP64-bound kernel)",
+        "l2": "256 MiB write between timed steps (the kernel streams nothing: its working set is KBs of shared memory "
+              "and registers, so L2 state does not matter; kept because the timing rules ask for it)",
     }
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
 def cpu_sample(args, seconds, threads):
     """Times the oracle (C restatement of the reference's rayon path) on `threads` host threads for
-    about `seconds`; returns (moves/s, moves, wall, flops_per_move, replicas)."""
+    about `seconds`; returns (moves/s, moves, wall, replicas).  The timed build is
+    oracle/libcp_oracle_fast.so (-O3 -march=native, no operation counters), made on this machine."""
     import orc
 
     state = orc.state_from_group(orc.polygon(args.sides), args.group, orc.MATH_LIBM)
     bopt = orc.build_optimiser(steps=args.mc_steps, inner_steps=args.inner_steps)
+    orc.lib_fast()  # build + load outside the timed region
     batch = threads
-    total_moves, total_wall, total_flops, done = 0, 0.0, 0.0, 0
+    total_moves, total_wall, done = 0, 0.0, 0
     cpu_sample.best = float("nan")
     while True:
         t0 = time.perf_counter()
-        _, best, res, cnt = orc.analyse_state(state, bopt, done, batch, n_threads=threads, want_counters=True)
+        _, best, res = orc.analyse_state_fast(state, bopt, done, batch, n_threads=threads)
         dt = time.perf_counter() - t0
         if not (cpu_sample.best >= best.score):
             cpu_sample.best = best.score
         total_wall += dt
         total_moves += sum(r.moves for r in res)
-        total_flops += orc.lib().orc_counters_flops(ctypes.byref(cnt))
         done += batch
         rate = done / total_wall
-        if total_wall >= seconds * 0.6 or done >= 4096:
+        if total_wall >= seconds * 0.6 or done >= 8192:
             break
         batch = max(threads, int(min(rate * (seconds - total_wall), 4 * done)) // threads * threads)
-    return total_moves / total_wall, total_moves, total_wall, total_flops / total_moves, done
+    return total_moves / total_wall, total_moves, total_wall, done
+
+
+def counted_flops_per_move(args, threads, replicas=64):
+    """Reference-formula operations per trial move (SURVEY.md 8d unit costs) on a small PCG sample,
+    from the counting build of the oracle; untimed."""
+    import orc
+
+    state = orc.state_from_group(orc.polygon(args.sides), args.group, orc.MATH_LIBM)
+    bopt = orc.build_optimiser(steps=args.mc_steps, inner_steps=args.inner_steps)
+    _, _, res, cnt = orc.analyse_state(state, bopt, 0, replicas, n_threads=threads, want_counters=True)
+    return orc.lib().orc_counters_flops(ctypes.byref(cnt)) / sum(r.moves for r in res)
 
 
 def run_reference(args, rank, world):
@@ -113,7 +136,7 @@ def run_reference(args, rank, world):
         cpu_sample(args, min(1.0, per_step), threads)
     walls, moves, reps = [], 0, 0
     for _ in range(args.steps):
-        v, m, w, _, n = cpu_sample(args, per_step, threads)
+        v, m, w, n = cpu_sample(args, per_step, threads)
         walls.append(w)
         moves += m
         reps += n
@@ -127,7 +150,8 @@ def run_reference(args, rank, world):
         "best_packing_fraction": cpu_sample.best,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference's rayon path (Rust toolchain absent: "
-                                 "the crate cannot be compiled here); gcc -O2 -ffp-contract=off, pthreads"},
+                                 "the crate cannot be compiled here); gcc -O3 -march=native -ffp-contract=off, "
+                                 "operation counters compiled out, pthreads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -190,24 +214,252 @@ def physical_gpu_index(local_rank):
 
 
 # ----------------------------------------------------------------------------- the B200 arm
+EXECUTED_PROFILE = os.path.join(ROOT, "profiles", "r2_executed_flops.json")
+
+
+class Bench:
+    """One rank of the B200 arm: engine, launch stream, process group."""
+
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+
+        import crystal_packing_b200 as cp
+        from crystal_packing_b200 import distributed as cpd
+
+        self.torch, self.cp, self.cpd = torch, cp, cpd
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference)")
+        torch.cuda.set_device(local_rank)
+        self.dev = f"cuda:{local_rank}"
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+        self.eng = cp.Engine(local_rank, lanes=args.lanes)
+        self.stream = torch.cuda.Stream(device=local_rank)
+        self.eng.set_stream(self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        _ = self.best_view()
+
+    def best_view(self):
+        """The ctx's device cp_best (allocated once by cp_init) as a uint8 tensor."""
+        cpd = self.cpd
+
+        class BestView:
+            def __init__(self, ptr):
+                self.__cuda_array_interface__ = {"shape": (cpd.BEST_BYTES,), "typestr": "|u1", "data": (ptr, False),
+                                                 "version": 2}
+
+        if not hasattr(self, "_best_dev"):
+            state = self.cp.PackedState.from_group(self.cp.LineShape.polygon(4), "p1")
+            self.eng.prepare(state._problem, self.cp.BuildOptimiser.cli_defaults().pipeline(), 32)
+            _, ptr = self.eng.device_buffers()
+            self._best_dev = self.torch.as_tensor(BestView(ptr), device=self.dev)
+        return self._best_dev
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_floats(self, xs):
+        """every rank's list of floats (same length on all ranks)"""
+        if not self.dist:
+            return [list(xs)]
+        t = self.torch.tensor(list(xs), dtype=self.torch.float64, device=self.dev)
+        out = self.torch.empty(self.world * len(xs), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)
+        v = out.cpu().tolist()
+        return [v[r * len(xs):(r + 1) * len(xs)] for r in range(self.world)]
+
+    def gather_best(self, local_u8):
+        """all-gather of cp_best records on the launch stream: the stream waits for the collective, so
+        the next launch (which overwrites the device cp_best) and the closing event are ordered after it"""
+        if not self.dist:
+            return local_u8
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            out = torch.empty(self.world * local_u8.numel(), dtype=torch.uint8, device=self.dev)
+            work = self.dist.all_gather_into_tensor(out, local_u8, async_op=True)
+            work.wait()  # the CURRENT stream (the launch stream) waits; the host does not
+        return out
+
+    def timed_passes(self, one_pass, warmup, steps, sample_clocks=False):
+        """warmup untimed passes, then `steps` passes each bracketed by CUDA events on the launch
+        stream (256 MiB L2 flush before the opening event), barrier + synchronize on both sides.
+        Returns (per-pass ms on this rank, max-over-ranks total ms, wall s, clocks)."""
+        torch = self.torch
+        for _ in range(warmup):
+            one_pass()
+        torch.cuda.synchronize()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(physical_gpu_index(self.local_rank))
+            sampler.start()
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall0 = time.perf_counter()
+        for a, b in ev:
+            with torch.cuda.stream(self.stream):
+                self.flush.fill_(1)
+                a.record(self.stream)
+            one_pass()
+            b.record(self.stream)
+            self.stream.synchronize()
+        self.barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        ms = [a.elapsed_time(b) for a, b in ev]
+        return ms, self.max_over_ranks(sum(ms)), wall, clocks
+
+
+def schedule_moves(schedules):
+    return sum((s.steps // s.inner_steps) * s.inner_steps for s in schedules)
+
+
+def run_weak_config(B, name, state, opts, per_gpu, note):
+    """C3 / C4: `per_gpu` replicas on every rank, device-resident, timed like the headline."""
+    cp, args = B.cp, B.args
+    schedules = opts.pipeline()
+    begin, _ = B.cpd.weak_range(per_gpu, B.rank)
+    B.eng.prepare(state._problem, schedules, per_gpu, replica_begin=begin, rng=cp.RNG_PHILOX)
+    best_dev = B.best_view()
+    kernel_ms = []
+
+    def one_pass():
+        B.eng.launch()
+        one_pass.gathered = B.gather_best(best_dev)
+
+    warm = max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        one_pass()
+    B.torch.cuda.synchronize()
+
+    def timed():
+        one_pass()
+        B.stream.synchronize()
+        kernel_ms.append(B.eng.timing_kernel_ms())
+
+    ms, total_ms, _, _ = B.timed_passes(timed, 0, args.config_steps)
+    moves = per_gpu * schedule_moves(schedules)
+    gbest = B.cpd.global_best(one_pass.gathered)
+    t = B.eng.timing()
+    return {
+        "workload": note, "scaling": "weak", "replicas_per_gpu": per_gpu, "global_replicas": per_gpu * B.world,
+        "moves_per_replica": schedule_moves(schedules), "value": B.world * moves * args.config_steps / (total_ms * 1e-3),
+        "unit": UNIT, "ms_per_step": total_ms / args.config_steps, "kernel_ms_rank0": sum(kernel_ms) / len(kernel_ms),
+        "steps": args.config_steps, "warmup": warm, "gpu_launches": 3 * args.config_steps,
+        "lanes_per_replica": t.lanes_per_replica, "best_score": gbest["score"], "best_replica": gbest["replica"],
+    }
+
+
+def run_c5(B):
+    """BASELINE.json configs[4]: 3..12-gons x the seven plane groups, a FIXED batch split over the
+    ranks (strong scaling).  Cells differ ~18x in cost per replica, so the cells are cut into chunks
+    and the chunks are dealt longest-first by MEASURED time: the first warm-up pass is the
+    calibration (chunk i timed by rank i mod N, times all-gathered), every later pass uses the
+    balanced assignment.  No data-path collective; one all-gather of the per-chunk best states."""
+    cp, cpd, args, torch = B.cp, B.cpd, B.args, B.torch
+    cells = cpd.sweep_cells()
+    per_cell = args.c5_total // len(cells)
+    opts = cp.BuildOptimiser.cli_defaults(steps=args.c5_mc_steps, inner_steps=min(1000, args.c5_mc_steps))
+    schedules = opts.pipeline()
+    mpr = schedule_moves(schedules)
+    states = [cp.PackedState.from_group(cp.LineShape.polygon(n), g) for n, g in cells]
+    est = [cpd.estimated_cell_cost(n, st.total_shapes()) for (n, g), st in zip(cells, states)]
+    chunks = cpd.sweep_chunks(est, per_cell, B.world)
+    best_dev = B.best_view()
+    slots = len(chunks)  # a rank never holds more chunks than there are
+    nan_rec = torch.frombuffer(bytearray(cpd.pack_best([0.0] * 6, float("nan"), 0, 0, 2 ** 64 - 1)), dtype=torch.uint8)
+    template = nan_rec.to(B.dev).repeat(slots)
+    torch.cuda.synchronize()
+
+    def run_chunks(mine, timed_each):
+        """launches this rank's chunks back to back; keeps each chunk's cp_best in its slot"""
+        with torch.cuda.stream(B.stream):
+            bests = template.clone()
+        times = {}
+        for k, ci in enumerate(mine):
+            c, begin, count = chunks[ci]
+            B.eng.prepare(states[c]._problem, schedules, count, replica_begin=begin, rng=cp.RNG_PHILOX)
+            B.eng.launch()
+            with torch.cuda.stream(B.stream):
+                bests[k * cpd.BEST_BYTES:(k + 1) * cpd.BEST_BYTES].copy_(best_dev)
+            if timed_each:
+                B.stream.synchronize()
+                times[ci] = B.eng.timing_kernel_ms()
+        return bests, times
+
+    # calibration = warm-up pass 1 (also loads every kernel build this rank will launch)
+    cal = cpd.round_robin_assign(len(chunks), B.world)
+    _, times = run_chunks(cal[B.rank], True)
+    mine_t = [times.get(i, 0.0) for i in range(len(chunks))]
+    measured = [max(col) for col in zip(*B.gather_floats(mine_t))]  # each chunk was timed by exactly one rank
+    assign, est_loads = cpd.lpt_assign(measured, B.world)
+    mine = assign[B.rank]
+    for ci in mine:  # load the builds of the final assignment outside the timed region
+        c, begin, _ = chunks[ci]
+        if ci not in times:
+            B.eng.prepare(states[c]._problem, schedules, 64, replica_begin=begin, rng=cp.RNG_PHILOX)
+            B.eng.launch()
+    B.torch.cuda.synchronize()
+    warm = max(1, min(args.warmup, 3) - 1)
+    state = {}
+
+    def one_pass():
+        bests, _ = run_chunks(mine, False)
+        state["gathered"] = B.gather_best(bests)
+
+    ms, total_ms, _, _ = B.timed_passes(one_pass, warm, args.config_steps)
+    per_rank = [v[0] for v in B.gather_floats([sum(ms) / len(ms)])]
+    # per-cell best over all chunks of all ranks
+    raw = state["gathered"].cpu().numpy().tobytes()
+    recs = [cpd.unpack_best(raw[i:i + cpd.BEST_BYTES]) for i in range(0, len(raw), cpd.BEST_BYTES)]
+    cell_best = {}
+    for r in range(B.world):
+        for k, ci in enumerate(assign[r]):
+            rec = recs[r * slots + k]
+            c = chunks[ci][0]
+            if rec["score"] == rec["score"] and (c not in cell_best or rec["score"] > cell_best[c]["score"] or (
+                    rec["score"] == cell_best[c]["score"] and rec["replica"] > cell_best[c]["replica"])):
+                cell_best[c] = rec
+    total_moves = per_cell * len(cells) * mpr
+    heavy = sorted(range(len(cells)), key=lambda c: -sum(measured[i] for i, ch in enumerate(chunks) if ch[0] == c))[:3]
+    cell_ms = {c: sum(measured[i] for i, ch in enumerate(chunks) if ch[0] == c) for c in range(len(cells))}
+    return {
+        "workload": f"polygon(3..12) x {{{','.join(cpd.SWEEP_GROUPS)}}}: 70 cells x {per_cell} replicas, 3-stage pipeline "
+                    f"(100 + {args.c5_mc_steps} + {args.c5_mc_steps} steps)",
+        "scaling": "strong", "global_replicas": per_cell * len(cells), "moves_per_replica": mpr,
+        "value": total_moves * args.config_steps / (total_ms * 1e-3), "unit": UNIT,
+        "wall_ms_per_pass": total_ms / args.config_steps, "per_rank_ms": per_rank,
+        "rank_spread": (max(per_rank) - min(per_rank)) / max(per_rank),
+        "chunks": len(chunks), "chunks_per_rank": [len(a) for a in assign],
+        "balance": "longest-first by measured chunk time (calibration = first warm-up pass)",
+        "planned_loads_ms": est_loads, "steps": args.config_steps, "warmup": warm + 1,
+        "gpu_launches": 3 * len(mine) * args.config_steps,
+        "limit": "heaviest cells: " + ", ".join(
+            f"{cells[c][0]}-gon/{cells[c][1]} {cell_ms[c]:.0f} ms" for c in heavy) +
+            f" of {sum(cell_ms.values()):.0f} ms summed over all cells",
+        "cells_with_a_packing": len(cell_best),
+        "best_of_sweep": max((v["score"] for v in cell_best.values()), default=None),
+    }
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
 
-    import crystal_packing_b200 as cp
-    from crystal_packing_b200 import capi, distributed as cpd
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    eng = cp.Engine(local_rank, lanes=args.lanes)
-    stream = torch.cuda.Stream(device=local_rank)
-    eng.set_stream(stream.cuda_stream)
+    B = Bench(args, rank, local_rank, world)
+    cp, cpd, capi, eng, stream = B.cp, B.cpd, B.cp.capi, B.eng, B.stream
 
     state = cp.PackedState.from_group(cp.LineShape.polygon(args.sides), args.group)
     schedules = cp.BuildOptimiser.cli_defaults(steps=args.mc_steps, inner_steps=args.inner_steps).pipeline()
@@ -215,58 +467,31 @@ def run_b200(args, rank, local_rank, world):
     begin, _ = cpd.weak_range(n, rank)
     mpr = moves_per_replica(args)
     moves_per_step_rank = n * mpr
-
     fp64_peak, fp32_peak = eng.measure_peaks()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
-    gathered = None
-
-    class BestView:  # wraps the device cp_best as a uint8 tensor for the collective
-        def __init__(self, ptr):
-            self.__cuda_array_interface__ = {"shape": (cpd.BEST_BYTES,), "typestr": "|u1", "data": (ptr, False),
-                                             "version": 2}
-
-    def one_step_resident():
-        nonlocal gathered
-        eng.launch()
-        if world > 1:
-            with torch.cuda.stream(stream):
-                gathered = cpd.all_gather_best(best_dev)
 
     # ---- device-resident metric ("value")
     eng.prepare(state._problem, schedules, n, replica_begin=begin, rng=cp.RNG_PHILOX)
-    _, best_ptr = eng.device_buffers()
-    best_dev = torch.as_tensor(BestView(best_ptr), device=f"cuda:{local_rank}")
+    best_dev = B.best_view()
+    hold = {}
+    kernel_ms = []
+
+    def one_step_resident():
+        eng.launch()
+        hold["gathered"] = B.gather_best(best_dev)
+
     for _ in range(args.warmup):
         one_step_resident()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, wall0 = [], time.perf_counter()
-    for a, b in ev:
-        with torch.cuda.stream(stream):
-            flush.fill_(1)
-            a.record(stream)
+
+    def timed():
         one_step_resident()
-        b.record(stream)
         stream.synchronize()
         kernel_ms.append(eng.timing_kernel_ms())
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
+
+    step_ms, total_ms, wall, clocks = B.timed_passes(timed, 0, args.steps, sample_clocks=True)
     best_local = eng.fetch()
+    lanes = eng.timing().lanes_per_replica
     if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        gbest = cpd.global_best(gathered)
+        gbest = cpd.global_best(hold["gathered"])
     else:
         gbest = {"score": best_local.result.score, "replica": best_local.replica,
                  "dof": list(best_local.result.dof)}
@@ -284,74 +509,120 @@ def run_b200(args, rank, local_rank, world):
             b = eng.run_host_buffers(state._problem, schedules, n, init.data_ptr(), out.data_ptr(),
                                      replica_begin=begin, rng=cp.RNG_PHILOX)
             if world > 1:
-                mine = torch.frombuffer(bytearray(bytes(b)), dtype=torch.uint8).to(f"cuda:{local_rank}")
+                mine = torch.frombuffer(bytearray(bytes(b)), dtype=torch.uint8).to(B.dev)
                 cpd.global_best(cpd.all_gather_best(mine))
             return b
 
         for _ in range(min(args.warmup, 1)):
             one_step_e2e()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
+        B.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             one_step_e2e()
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        if dist:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = B.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * moves_per_step_rank * args.steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * e2e_s / args.steps,
                "api": "cp_run(ctx, problem, stages, 3, PHILOX, ..., init_dof=pinned host, out_all=pinned host)"}
 
+    # ---- the other BASELINE configurations
+    configs = {}
+    wanted = [c.strip().lower() for c in args.configs.split(",") if c.strip()]
+    if "c3" in wanted:
+        st3 = cp.PackedState.from_group(cp.MolecularShape2.from_trimer(0.637556, 120.0, 1.0), "p2gg")
+        o3 = cp.BuildOptimiser.cli_defaults(steps=args.mc_steps, inner_steps=args.inner_steps, kt_finish=0.001)
+        configs["C3"] = run_weak_config(B, "C3", st3, o3, 262144,
+                                        f"MolecularShape2 trimer(0.637556, 120, 1) in p2gg, 262144 replicas/GPU, annealed "
+                                        f"(kt 0.1 -> 0.001 over {args.mc_steps} steps), 3-stage pipeline")
+    if "c4" in wanted:
+        st4 = cp.PotentialState.from_group(cp.LJShape2.from_trimer(0.637556, 120.0, 1.0), "p2gg")
+        o4 = cp.BuildOptimiser.cli_defaults(steps=args.mc_steps, inner_steps=args.inner_steps)
+        configs["C4"] = run_weak_config(B, "C4", st4, o4, 131072,
+                                        f"LJShape2 trimer in p2gg (PotentialState, energy minimisation), 131072 replicas/GPU "
+                                        f"(1,048,576 on 8 GPUs), 3-stage pipeline 100 + {args.mc_steps} + {args.mc_steps}")
+    if "c5" in wanted:
+        configs["C5"] = run_c5(B)
+
     # ---- CPU baseline + algorithmic FLOPs per move (rank 0, N=1 only for the baseline figure)
     cpu, flops_per_move = None, None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, m, w, fpm, reps = cpu_sample(args, args.cpu_seconds if world == 1 else 3.0, threads)
-        flops_per_move = fpm
+        flops_per_move = counted_flops_per_move(args, threads)
         if world == 1:
+            v, m, w, reps = cpu_sample(args, args.cpu_seconds, threads)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{reps} replicas (seeds 0..{reps - 1}) of the same workload, full 3-stage schedule, "
                              f"{w:.1f} s wall",
                    "best_packing_fraction": cpu_sample.best,
-                   "note": "C restatement of the reference's rayon path; the Rust crate cannot be built here; "
-                           "its best packing is over the sample's replicas only (PCG stream)"}
+                   "note": "C restatement of the reference's rayon path (gcc -O3 -march=native, -ffp-contract=off, no "
+                           "operation counters); the Rust crate cannot be built here; its best packing is over the "
+                           "sample's replicas only (PCG stream)"}
     roofline = None
     if rank == 0:
         k_ms = sum(kernel_ms) / len(kernel_ms)
         if flops_per_move is not None:
             achieved = flops_per_move * moves_per_step_rank / (k_ms * 1e-3) / 1e12
             roofline = {
-                "bound": "fp64", "kernel": ("mc_thread_kernel<POLYGON,%d,PHILOX>" % (args.sides if 3 <= args.sides <= 12 else 0)) if eng.timing().lanes_per_replica == 1 else "mc_kernel<POLYGON,%d,PHILOX>" % eng.timing().lanes_per_replica, "achieved": achieved, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                "traffic": 1410560, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                                   "(profiles/r1_f_thread_end_of_round.txt); algorithmic HBM bytes are the 4.7 MB of results",
+                "bound": "fp64",
+                "kernel": ("mc_thread_kernel<POLYGON,%d,PHILOX>" % (args.sides if 3 <= args.sides <= 12 else 0))
+                if lanes == 1 else "mc_kernel<POLYGON,%d,PHILOX>" % lanes,
+                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak if fp64_peak else None,
                 "peak_source": "measured here: FP64 FMA chains, 2 flops/FMA (MEASURED_PEAKS.json has no FP64 entry)",
                 "fp32_fma_peak_tflops": fp32_peak, "frac_of_fp32_peak": achieved / fp32_peak if fp32_peak else None,
                 "flops_per_move": flops_per_move,
-                "flops_definition": "executed reference-formula operations per trial move counted by the oracle "
-                                    "(SURVEY.md §8d unit costs), not the instructions the kernel issues",
+                "flops_definition": "REFERENCE-EQUIVALENT work: operations the reference's formulas execute per trial "
+                                    "move, counted by the oracle (SURVEY.md 8d unit costs) - not the instructions this "
+                                    "kernel issues (it prunes the image sweep, decides most shape pairs with f32 "
+                                    "certificates and skips check_intersection for moves the Metropolis rule rejects)",
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (sum(step_ms) / len(step_ms)),
                 "moves_per_launch": moves_per_step_rank,
+                "hbm_note": "no HBM streaming on this path: the algorithmic bytes of a launch are its results "
+                            f"({n * ctypes.sizeof(capi.ReplicaResult)} B written once) and, in e2e, the initial DOFs",
             }
+            # what the kernel actually executes, from the committed ncu capture of this same command
+            traffic = None
+            try:
+                prof = json.load(open(EXECUTED_PROFILE))
+                key = f"polygon({args.sides})/{args.group}/{args.replicas}/{mpr}"
+                ex = prof.get(key)
+                if ex and lanes == 1:
+                    f64, f32 = ex["fp64_flops_per_move"], ex["fp32_flops_per_move"]
+                    moves_s = moves_per_step_rank / (k_ms * 1e-3)
+                    roofline.update({
+                        "executed_fp64_flops_per_move": f64, "executed_fp32_flops_per_move": f32,
+                        "frac_executed": f64 * moves_s / 1e12 / fp64_peak if fp64_peak else None,
+                        "frac_executed_fp32": f32 * moves_s / 1e12 / fp32_peak if fp32_peak else None,
+                        "issue_slots_busy": ex["issue_active_pct"] / 100.0,
+                        "warp_instructions_per_move": ex["warp_instructions_per_move"],
+                        "active_lanes_per_instruction": ex["thread_inst_per_inst"],
+                        "from_profile": ex["from_profile"],
+                        "executed_note": "per-move instruction counts of the ncu capture x this run's moves/s; the kernel "
+                                         "is bound by issue slots and fixed-latency dependencies at ~3 warps per "
+                                         "scheduler, not by an FP pipe",
+                    })
+                    traffic = ex["dram_bytes_per_launch"]
+            except (OSError, ValueError, KeyError):
+                pass
+            roofline["traffic"] = traffic
+            roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, "
+                                        "from the profile named in from_profile" if traffic is not None else
+                                        "no ncu capture committed for this workload")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": 3 * args.steps, "lanes_per_replica": eng.timing().lanes_per_replica,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": 3 * args.steps, "lanes_per_replica": lanes,
+            "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
             "best_packing_fraction": gbest["score"], "best_replica": gbest["replica"],
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)
-    if dist:
-        dist.barrier()
-        dist.destroy_process_group()
+    if B.dist:
+        B.dist.barrier()
+        B.dist.destroy_process_group()
 
 
 def main():

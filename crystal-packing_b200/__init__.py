@@ -23,6 +23,7 @@ from .api import (  # noqa: F401
     LJShape2,
     LineShape,
     MCOptimiser,
+    MultiEngine,
     MolecularShape2,
     PackedState,
     PackedState2,

@@ -312,6 +312,54 @@ class Engine:
         return [[out[r * m + k] for k in range(m)] for r in range(n)]
 
 
+class MultiEngine:
+    """One cp_multi: a list of GPUs behind one handle (cp_init_multi).  `run` has the signature of
+    Engine.run; the replicas are sharded contiguously over the devices and the best state is the
+    one a single device would return."""
+
+    def __init__(self, devices):
+        self._lib = load_library()
+        self.devices = list(devices)
+        ids = (C.c_int * len(self.devices))(*self.devices)
+        self._m = C.c_void_p()
+        _check(self._lib.cp_init_multi(ids, len(self.devices), C.byref(self._m)))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.cp_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, problem, schedules, n_replicas, replica_begin=0, seed_base=0, rng=RNG_PCG64MCG,
+            init_dof=None, want_all=True):
+        sched = (capi.Schedule * len(schedules))(*schedules)
+        init = None
+        if init_dof is not None:
+            init = (C.c_double * (6 * n_replicas))(*[v for d in init_dof for v in d])
+        best = capi.Best()
+        out_all = (capi.ReplicaResult * n_replicas)() if want_all else None
+        _check(self._lib.cp_multi_run(self._m, C.byref(problem), sched, len(schedules), rng, seed_base,
+                                      replica_begin, n_replicas, init, C.byref(best), out_all))
+        return best, out_all
+
+    def shards(self):
+        """(replica_begin, n_replicas, kernel_ms) of every device in the last run."""
+        out = []
+        for k in range(len(self.devices)):
+            b, n = C.c_uint64(), C.c_uint64()
+            _check(self._lib.cp_multi_shard(self._m, k, C.byref(b), C.byref(n)))
+            ctx, t = C.c_void_p(), capi.Timing()
+            _check(self._lib.cp_multi_context(self._m, k, C.byref(ctx)))
+            _check(self._lib.cp_last_timing(ctx, C.byref(t)))
+            out.append((b.value, n.value, t.kernel_ms))
+        return out
+
+
 _default_engine = None
 
 
@@ -474,7 +522,7 @@ def monte_carlo_best_packing(state, optimiser, replications, engine=None, rng=RN
     """GPU drop-in for the CLI's analyse_state (main.rs:215-269): `replications` independent
     replicas (seed = replica index) through the three-stage pipeline, then the max by score.
     Returns the best state (and, optionally, every replica's result)."""
-    eng = engine or default_engine()
+    eng = engine or default_engine()  # an Engine (one GPU) or a MultiEngine (a list of GPUs)
     best, out_all = eng.run(state._problem, optimiser.pipeline(), replications,
                             replica_begin=replica_begin, seed_base=0, rng=rng, want_all=return_all)
     if math.isnan(best.result.score):

@@ -125,6 +125,13 @@ SIGNATURES = {
     "cp_replay": (_i, [_ctx, _P(Problem), _P(_d), _P(Move), _u64, _u64, _P(Decision)]),
     "cp_replay_bounded": (_i, [_ctx, _P(Problem), _P(_d), _P(_d), _P(Move), _u64, _u64, _P(Decision)]),
     "cp_images": (_i, [_ctx, _P(Problem), _P(_d), _u64, _P(_d)]),
+    "cp_init_multi": (_i, [_P(_i), _i, _P(_ctx)]),
+    "cp_multi_destroy": (None, [_ctx]),
+    "cp_multi_device_count": (_i, [_ctx, _P(_i)]),
+    "cp_multi_context": (_i, [_ctx, _i, _P(_ctx)]),
+    "cp_multi_shard": (_i, [_ctx, _i, _P(_u64), _P(_u64)]),
+    "cp_multi_run": (_i, [_ctx, _P(Problem), _P(Schedule), _i, _i, _u64, _u64, _u64, _P(_d), _P(Best),
+                          _P(ReplicaResult)]),
 }
 
 

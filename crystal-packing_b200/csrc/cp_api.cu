@@ -238,6 +238,20 @@ cp_status cp_device_count(int *out) {
     return CP_OK;
 }
 
+static cp_status init_members(cp_ctx *ctx, int device) {
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CP_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CP_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto &ev : ctx->ev) CP_CUDA(cudaEventCreate(&ev));
+    CP_CUDA(cudaMalloc(&ctx->d_partial, sizeof(BestKey) * (kPartials + 1)));
+    CP_CUDA(cudaMalloc(&ctx->d_error, sizeof(int)));
+    CP_CUDA(cudaMalloc(&ctx->d_best, sizeof(cp_best)));
+    return CP_OK;
+}
+
 cp_status cp_init(int device, cp_ctx **out) {
     if (!out) return cp_fail(CP_ERR_INVALID_ARG, "cp_init: null output");
     *out = nullptr;
@@ -249,16 +263,14 @@ cp_status cp_init(int device, cp_ctx **out) {
     CP_CUDA(cudaSetDevice(device));
     cp_ctx *ctx = new (std::nothrow) cp_ctx();
     if (!ctx) return cp_fail(CP_ERR_CUDA, "out of host memory");
-    ctx->device = device;
-    cudaDeviceProp prop;
-    CP_CUDA(cudaGetDeviceProperties(&prop, device));
-    ctx->sm_count = prop.multiProcessorCount;
-    CP_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    ctx->stream = ctx->own_stream;
-    for (auto &ev : ctx->ev) CP_CUDA(cudaEventCreate(&ev));
-    CP_CUDA(cudaMalloc(&ctx->d_partial, sizeof(BestKey) * (kPartials + 1)));
-    CP_CUDA(cudaMalloc(&ctx->d_error, sizeof(int)));
-    CP_CUDA(cudaMalloc(&ctx->d_best, sizeof(cp_best)));
+    const cp_status st = init_members(ctx, device);
+    if (st != CP_OK) {  // a half-built context is released here: the caller never sees it
+        const std::string why = g_last_error;
+        cp_destroy(ctx);
+        (void)cudaGetLastError();
+        g_last_error = why;
+        return st;
+    }
     *out = ctx;
     return CP_OK;
 }
@@ -266,7 +278,7 @@ cp_status cp_init(int device, cp_ctx **out) {
 void cp_destroy(cp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_out);
     cudaFree(ctx->d_init);
     cudaFree(ctx->d_partial);
@@ -438,6 +450,126 @@ cp_status cp_run(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stag
     if (st == CP_OK) st = cp_launch(ctx);
     if (st == CP_OK) st = cp_fetch(ctx, out_best, out_all);
     return st;
+}
+
+// ---- several GPUs behind one handle -------------------------------------------------------------
+// analyse_state's replica loop (main.rs:221-253) over a list of devices: the range of replicas is cut
+// into contiguous shards, one per device, every device runs its shard on its own stream at the same
+// time (prepare + launch are asynchronous; one host thread drives them all), and the per-device
+// maxima are reduced on the host.  The seed of a replica is its global index, so the result does not
+// depend on the number of devices.
+// The reduction is n x 80 bytes that cp_fetch has already copied to the host (the caller wants
+// out_best in host memory anyway), so a device-side collective would only add a launch and a second
+// synchronisation to every call; processes that keep their results on the device (one process per
+// GPU, bench.py) all-gather the cp_best of cp_device_buffers over NCCL instead.
+struct cp_multi {
+    std::vector<cp_ctx *> ctx;
+    std::vector<uint64_t> begin, count;  // shards of the last run (global replica indices)
+};
+
+static bool host_better(const cp_best &a, const cp_best &b) {  // the rule of better() above
+    if (!(a.result.score == a.result.score)) return false;
+    if (!(b.result.score == b.result.score)) return true;
+    return a.result.score > b.result.score || (a.result.score == b.result.score && a.replica > b.replica);
+}
+
+cp_status cp_init_multi(const int *device_ids, int n_devices, cp_multi **out) {
+    if (!out) return cp_fail(CP_ERR_INVALID_ARG, "cp_init_multi: null output");
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > 64)
+        return cp_fail(CP_ERR_INVALID_ARG, "cp_init_multi: need 1..64 device ids");
+    cp_multi *m = new (std::nothrow) cp_multi();
+    if (!m) return cp_fail(CP_ERR_CUDA, "out of host memory");
+    for (int k = 0; k < n_devices; ++k) {
+        cp_ctx *c = nullptr;
+        const cp_status st = cp_init(device_ids[k], &c);
+        if (st != CP_OK) {
+            const std::string why = g_last_error;
+            cp_multi_destroy(m);
+            g_last_error = why;
+            return st;
+        }
+        m->ctx.push_back(c);
+    }
+    m->begin.assign(n_devices, 0);
+    m->count.assign(n_devices, 0);
+    *out = m;
+    return CP_OK;
+}
+
+void cp_multi_destroy(cp_multi *m) {
+    if (!m) return;
+    for (cp_ctx *c : m->ctx) cp_destroy(c);
+    delete m;
+}
+
+cp_status cp_multi_device_count(const cp_multi *m, int *out) {
+    if (!m || !out) return cp_fail(CP_ERR_INVALID_ARG, "cp_multi_device_count: null argument");
+    *out = (int)m->ctx.size();
+    return CP_OK;
+}
+
+cp_status cp_multi_context(cp_multi *m, int k, cp_ctx **out) {
+    if (!m || !out || k < 0 || k >= (int)m->ctx.size())
+        return cp_fail(CP_ERR_INVALID_ARG, "cp_multi_context: index out of range");
+    *out = m->ctx[k];
+    return CP_OK;
+}
+
+cp_status cp_multi_shard(const cp_multi *m, int k, uint64_t *replica_begin, uint64_t *n_replicas) {
+    if (!m || k < 0 || k >= (int)m->ctx.size()) return cp_fail(CP_ERR_INVALID_ARG, "cp_multi_shard: index out of range");
+    if (replica_begin) *replica_begin = m->begin[k];
+    if (n_replicas) *n_replicas = m->count[k];
+    return CP_OK;
+}
+
+cp_status cp_multi_run(cp_multi *m, const cp_problem *problem, const cp_schedule *stages, int n_stages, int rng_mode,
+                       uint64_t seed_base, uint64_t replica_begin, uint64_t n_replicas, const double *init_dof,
+                       cp_best *out_best, cp_replica_result *out_all) {
+    if (!m) return cp_fail(CP_ERR_INVALID_ARG, "cp_multi_run: null handle");
+    if (n_replicas == 0) return cp_fail(CP_ERR_INVALID_ARG, "cp_multi_run: n_replicas must be > 0");
+    const uint64_t nd = m->ctx.size();
+    const uint64_t base = n_replicas / nd, extra = n_replicas % nd;
+    uint64_t at = 0;
+    for (uint64_t k = 0; k < nd; ++k) {  // contiguous shards, the first `extra` of them one replica longer
+        m->begin[k] = replica_begin + at;
+        m->count[k] = base + (k < extra ? 1 : 0);
+        at += m->count[k];
+    }
+    // every device is started before any is waited for
+    for (uint64_t k = 0; k < nd; ++k) {
+        if (m->count[k] == 0) continue;
+        const uint64_t off = m->begin[k] - replica_begin;
+        cp_status st = cp_prepare(m->ctx[k], problem, stages, n_stages, rng_mode, seed_base, m->begin[k], m->count[k],
+                                  init_dof ? init_dof + off * CP_MAX_DOF : nullptr);
+        if (st == CP_OK) st = cp_launch(m->ctx[k]);
+        if (st != CP_OK) {
+            const std::string why = g_last_error;
+            for (uint64_t j = 0; j < k; ++j)
+                if (m->count[j]) cp_synchronize(m->ctx[j]);
+            g_last_error = why;
+            return st;
+        }
+    }
+    cp_status first_error = CP_OK;
+    std::string why;
+    cp_best best{};
+    best.result.score = std::nan("");
+    best.replica = ~0ull;
+    for (uint64_t k = 0; k < nd; ++k) {
+        if (m->count[k] == 0) continue;
+        cp_best b{};
+        const uint64_t off = m->begin[k] - replica_begin;
+        const cp_status st = cp_fetch(m->ctx[k], &b, out_all ? out_all + off : nullptr);
+        if (st != CP_OK && first_error == CP_OK) {
+            first_error = st;
+            why = g_last_error;
+        }
+        if (st == CP_OK && host_better(b, best)) best = b;
+    }
+    if (out_best) *out_best = best;
+    if (first_error != CP_OK) g_last_error = why;
+    return first_error;
 }
 
 cp_status cp_measure_peaks(cp_ctx *ctx, double *fp64_tflops, double *fp32_tflops) {

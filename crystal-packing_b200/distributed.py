@@ -60,6 +60,37 @@ def lpt_assign(costs, world):
     return mine, loads
 
 
+def estimated_cell_cost(sides, n_syms):
+    """Relative cost of one replica of a cell, from the one-GPU table (profiles/r2_c5_sweep.txt):
+    only decides into how many chunks a cell is cut; the assignment itself uses measured times."""
+    return {1: 0.05, 2: 0.075}.get(n_syms, 0.24) * (1.0 + 0.2 * (sides - 3))
+
+
+def sweep_chunks(cell_costs, replicas_per_cell, world, granularity=6, min_chunk=16384):
+    """Cuts the cells into chunks (cell, replica_begin, count): a cell whose estimated cost exceeds
+    1/granularity of one rank's share of the whole sweep is cut into pieces below that size (never
+    below `min_chunk` replicas: a launch that does not fill the GPU wastes it).  world = 1 cuts
+    nothing.  Seeds are the replica's index within its cell, so the cut does not change any result."""
+    total = sum(cell_costs)
+    target = total / (world * granularity)
+    out = []
+    for c, cost in enumerate(cell_costs):
+        k = 1
+        if world > 1 and cost > target:
+            k = min(-(-cost // target), max(1, replicas_per_cell // min_chunk))
+        k = int(k)
+        for j in range(k):
+            begin, count = shard_range(replicas_per_cell, j, k)
+            if count:
+                out.append((c, begin, count))
+    return out
+
+
+def round_robin_assign(n_items, world):
+    """Calibration pass: chunk i is measured by rank i % world."""
+    return [list(range(r, n_items, world)) for r in range(world)]
+
+
 def pack_best(dof, score, rejections, moves, replica):
     return struct.pack(_FMT, *dof, score, rejections, moves, replica)
 

@@ -11,7 +11,8 @@
  * Conventions: plain pointers and sizes, caller owns every buffer, every function returns a
  * cp_status (0 = ok) and never throws; f64 everywhere (the reference is f64 end to end);
  * Option<f64> is encoded as NaN = None.  A cp_ctx is bound to ONE GPU and is not thread-safe: use
- * one ctx (and one host thread or process) per GPU.  There is no CPU fallback: without a usable
+ * one ctx (and one host thread or process) per GPU, or a cp_multi (below), which owns one ctx per
+ * device and drives them from the calling thread.  There is no CPU fallback: without a usable
  * CUDA device cp_init fails with CP_ERR_NO_DEVICE.
  */
 #ifndef CP_GPU_H
@@ -188,7 +189,16 @@ cp_status cp_run(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stag
 
 /* the same split in three so a caller can keep everything resident in HBM:
  * prepare = allocate + upload, launch = kernels only (asynchronous on the ctx stream),
- * fetch = synchronise + copy back. */
+ * fetch = synchronise + copy back.
+ * Buffer lifetimes the split leaves to the caller:
+ *  - cp_prepare ENQUEUES the copy of init_dof on the ctx stream and returns: a pinned init_dof must
+ *    stay valid and unchanged until the stream has passed the copy (cp_synchronize, cp_fetch, or
+ *    any later synchronisation of that stream); pageable memory is staged before the call returns.
+ *  - every cp_launch overwrites the device results and the device cp_best of the previous launch;
+ *    work on OTHER streams that reads them (a collective on the communicator's stream, a peer copy)
+ *    must be ordered before the next cp_launch by the caller (event or stream wait).
+ *  - the addresses returned by cp_device_buffers go stale when a cp_prepare with more replicas than
+ *    any before it reallocates the result buffer; ask again after every cp_prepare. */
 cp_status cp_prepare(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stages,
                      int n_stages, int rng_mode, uint64_t seed_base, uint64_t replica_begin,
                      uint64_t n_replicas, const double *init_dof);
@@ -200,6 +210,26 @@ cp_status cp_synchronize(cp_ctx *ctx);
  * multi-GPU host hand the best state to its collective (NCCL) without a host round trip. */
 cp_status cp_device_buffers(cp_ctx *ctx, void **d_results, void **d_best);
 cp_status cp_last_timing(cp_ctx *ctx, cp_timing *out);
+
+/* ---- several GPUs behind one handle ----
+ * The replica loop of analyse_state (main.rs:221-253: `(0..replications).into_par_iter()...max()`)
+ * over a list of CUDA devices: [replica_begin, replica_begin + n_replicas) is cut into contiguous
+ * shards, one per entry of device_ids (an id may repeat: two contexts, two streams on that GPU);
+ * all devices run at the same time, driven by the calling thread; the per-device maxima (80 bytes
+ * each, already on the host) are reduced on the host by the rule of cp_best.  Seeds are global
+ * replica indices, so the answer is the one a single device gives.  init_dof / out_all cover the
+ * whole range, as in cp_run.  Not thread-safe, like cp_ctx. */
+typedef struct cp_multi cp_multi;
+cp_status cp_init_multi(const int *device_ids, int n_devices, cp_multi **out);
+void cp_multi_destroy(cp_multi *m);
+cp_status cp_multi_device_count(const cp_multi *m, int *out);
+/* the k-th device's context, owned by the handle (cp_last_timing, cp_set_lanes, cp_score ...) */
+cp_status cp_multi_context(cp_multi *m, int k, cp_ctx **out);
+/* the shard the k-th device ran in the last cp_multi_run */
+cp_status cp_multi_shard(const cp_multi *m, int k, uint64_t *replica_begin, uint64_t *n_replicas);
+cp_status cp_multi_run(cp_multi *m, const cp_problem *problem, const cp_schedule *stages, int n_stages,
+                       int rng_mode, uint64_t seed_base, uint64_t replica_begin, uint64_t n_replicas,
+                       const double *init_dof, cp_best *out_best, cp_replica_result *out_all);
 
 /* Measured FP64 / FP32 FMA throughput of this GPU (2 flops per FMA, register-resident chains):
  * the roofline denominators bench.py reports against (no reference counterpart). */

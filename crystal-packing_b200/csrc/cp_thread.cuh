@@ -553,7 +553,7 @@ __device__ __forceinline__ double t_state_score(const KProblem &P, const TView &
                                                 const Trig &t, bool live) {
     if constexpr (KIND == CP_LJ) {
         const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
-        return t_lj_score<NI>(P, g, d, t, cell_cache_of(d));
+        return t_lj_score<NI>(P, g, d, t, cell_cache_of(d), live);
     } else {
         TCands<NS> c;
         c.sh = v.masks + threadIdx.x;
@@ -570,7 +570,7 @@ __device__ __forceinline__ double t_state_score(const KProblem &P, const TView &
 // shared memory of a block
 template <int KIND, int NI, int NS>
 __host__ __device__ inline size_t thread_block_shared_bytes(int n_items, int n_syms) {
-    if (KIND == CP_LJ) return sizeof(double) * kThreadBlock * (size_t)lj_geo_doubles(n_items, n_syms);
+    if (KIND == CP_LJ) return lj_block_bytes(n_items, n_syms);
     return TLayout<KIND, NI, NS>(n_items, n_syms).bytes();
 }
 
@@ -804,13 +804,15 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
                 }
             }
             if (slot <= 2) cc = cell_cache_of(d);
-            if constexpr (KIND == CP_LJ) {
-                const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
-                new_score = t_lj_score<NI>(P, g, d, t, cc);
-            } else {
+            if constexpr (KIND != CP_LJ) {
                 t_place<KIND, NI, NS>(P, v, d, t);
                 t_sweep<KIND, NI, NS>(P, v, d, t, cc, cands);
             }
+        }
+        if constexpr (KIND == CP_LJ) {  // whole warp: lanes without a proposal keep step
+            const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
+            const double s = t_lj_score<NI>(P, g, d, t, cc, have);
+            if (have) new_score = s;
         }
         // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
         bool overlap = false;

@@ -5,16 +5,56 @@
 
 #include "cp_device.cuh"
 
-// doubles of shared memory each LJ thread needs: four cell values, per image fx fy cx cy, per site
-// the rotated position
-__host__ __device__ inline int lj_geo_doubles(int n_items, int n_syms) { return 4 + n_syms * 4 + n_syms * n_items * 2; }
+// the filtered evaluation (t_lj_score_pooled) serves shapes of up to this many sites; larger shapes
+// and sites without cutoff take the plain loops
+constexpr int kLjQueueSites = 4;
 
-struct TGeo {
-    double *base;  // element e of this thread is base[e * 32]
+// doubles of shared memory each LJ thread needs: four cell values, per image fx fy cx cy, per site
+// the rotated position (f64), then the same positions in single precision (one double = x, y of a
+// site), the image masks of the shape pairs i < j and of a shape with itself (64 bits each) and two
+// elements of single-precision sweep parameters (af, bxf | byf, ec).  The warp's pool (32 entries,
+// 32 energies) follows the 32 columns.
+__host__ __device__ inline int lj_mask_words(int n_syms) { return n_syms * (n_syms - 1) / 2 + 1; }
+__host__ __device__ inline int lj_geo_doubles(int n_items, int n_syms) {
+    return 4 + n_syms * 4 + n_syms * n_items * 2 + n_syms * n_items + lj_mask_words(n_syms) + 2;
+}
+__host__ __device__ inline size_t lj_block_bytes(int n_items, int n_syms) {
+    return sizeof(double) * 32 * (size_t)(lj_geo_doubles(n_items, n_syms) + 1) + 32 * sizeof(unsigned);
+}
+
+// a thread's column of the [element][thread] planes (STRIDE = 32)
+template <int STRIDE>
+struct TGeoT {
+    double *base;  // element e is base[e * STRIDE]
     int comp0;     // first component element (= 4 + N * 4); images start at element 4
-    __device__ __forceinline__ double ld(int e) const { return base[e * 32]; }
-    __device__ __forceinline__ void st(int e, double v) const { base[e * 32] = v; }
+    __device__ __forceinline__ double ld(int e) const { return base[e * STRIDE]; }
+    __device__ __forceinline__ void st(int e, double v) const { base[e * STRIDE] = v; }
+    // single-precision copy of the rotated site c (= image * n + site): element comp0 + 2 * total + c
+    __device__ __forceinline__ float2 ldf(int total, int c) const {
+        return *reinterpret_cast<const float2 *>(base + (comp0 + 2 * total + c) * STRIDE);
+    }
+    __device__ __forceinline__ void stf(int total, int c, float x, float y) const {
+        *reinterpret_cast<float2 *>(base + (comp0 + 2 * total + c) * STRIDE) = make_float2(x, y);
+    }
+    // image mask m: element comp0 + 3 * total + m
+    __device__ __forceinline__ unsigned long long *mask(int total, int m) const {
+        return reinterpret_cast<unsigned long long *>(base + (comp0 + 3 * total + m) * STRIDE);
+    }
+    // sweep parameters: two elements behind the masks
+    __device__ __forceinline__ float2 *fpar(int total, int n_syms, int e) const {
+        return reinterpret_cast<float2 *>(base + (comp0 + 3 * total + lj_mask_words(n_syms) + e) * STRIDE);
+    }
+    // the same column of another lane of the warp
+    __device__ __forceinline__ TGeoT of(unsigned lane) const { return TGeoT{base - threadIdx.x + lane, comp0}; }
+    // the warp's pool behind the 32 columns (call on the lane's OWN column): 32 energies, 32 entries
+    __device__ __forceinline__ double *pool_energies(int n_items, int n_syms) const {
+        return base - threadIdx.x + 32 * lj_geo_doubles(n_items, n_syms);
+    }
+    __device__ __forceinline__ unsigned *pool_entries(int n_items, int n_syms) const {
+        return reinterpret_cast<unsigned *>(pool_energies(n_items, n_syms) + 32);
+    }
 };
+using TGeo = TGeoT<32>;
 
 // per-replica values that depend on the cell DOFs only, kept across moves
 struct CellCache {
@@ -57,8 +97,10 @@ __device__ __forceinline__ void lj_build_geometry(const KProblem &P, TGeo g, con
             if (NI == 0 && k >= n) break;
             const double *it = P.items[k];
             const int e = g.comp0 + (s * n + k) * CW;
-            g.st(e + 0, m00 * it[0] + m01 * it[1]);  // Transform * Point without its translation
-            g.st(e + 1, m10 * it[0] + m11 * it[1]);
+            const double rx = m00 * it[0] + m01 * it[1], ry = m10 * it[0] + m11 * it[1];
+            g.st(e + 0, rx);  // Transform * Point without its translation
+            g.st(e + 1, ry);
+            g.stf(N * n, s * n + k, (float)rx, (float)ry);  // the pre-filter's copy (t_lj_score)
         }
     }
 }
@@ -89,15 +131,13 @@ __device__ __forceinline__ double t_shape_energy(const KProblem &P, TGeo g, int 
     return e;
 }
 
-// PotentialState::score (state/potential.rs:82-115) for one replica in one thread: the reference's
-// accumulation order is simply the loop order here.  Exact pruning: when every site has a cutoff,
+// PotentialState::score (state/potential.rs:82-115) for one replica in one thread, plain loops (shapes
+// of more than kLjQueueSites sites): the reference's accumulation order is simply the loop order here.  Exact pruning: when every site has a cutoff,
 // a shape pair whose centres are further apart than max cutoff + 2 max|site| (P.lj_reach, widened
 // by 1e-9) has all its site distances beyond the cutoff, each LJ2::energy is exactly 0.0 and adding
 // it cannot change the sum - so the pair, its row or its columns are skipped outright.
 template <int NI>
-__device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Dof &d, const Trig &t,
-                                             const CellCache &cc) {
-    lj_build_geometry<NI>(P, g, d, t);
+__device__ __noinline__ double t_lj_score_plain(const KProblem &P, TGeo g, const Dof &d, const Trig &t) {
     const int N = P.n_syms;
     const double a = d.v[0], b = d.v[0] * d.v[1];
     const double reach = P.lj_reach * (1.0 + 1e-9);  // +inf: no pruning
@@ -151,6 +191,262 @@ __device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Do
         }
     }
     return -sum / (double)N;
+}
+
+// ---------------------------------------------------------------------------------- filtered, pooled evaluation
+// The same sum for shapes of up to kLjQueueSites sites, organised for SIMT.
+//   1. every lane sweeps the 48 images of its shape pairs in single precision into bit masks of the
+//      images whose centre can be within reach (a superset: an image outside the mask has every site
+//      distance beyond every cutoff, so each LJ2::energy is exactly 0.0 and the sum is unchanged;
+//      an extra image inside the mask only costs its tests).  One sweep per pair i < j - the mask of
+//      (j, i) is its mirror image - and one for a shape with itself;
+//   2. the candidate images of all 32 replicas are drawn, in rounds, into a pool of 32 entries, each
+//      replica's in the reference's order (potential.rs:88-110: in-cell pairs i < j, then i, j, x
+//      outer, y inner).  Each lane takes ONE entry, whoever owns it: it pre-filters the n x n site
+//      pairs in single precision against (cutoff + margin)^2 - again a superset of the pairs inside
+//      their cutoff - and evaluates the survivors (a few dozen per move out of ~7,000) with the
+//      reference's f64 expressions, cutoff test included (lj2.rs:43-60), adding them up in iproduct
+//      order: that is the energy of one shape pair (lj_shape.rs:35-39);
+//   3. the owner adds the shape-pair energies of its entries to its sum, in order.
+// Why a pool: the replicas of a warp differ enormously in the work one score needs.  Most sit in
+// dilute cells with a handful of images in reach, a few have collapsed into dense, elongated cells
+// with dozens (measured after 2,000 steps of the trimer in p2gg: 2 images for 85 % of the replicas,
+// 12 to 42 for the rest), and a loop per thread runs at the pace of the busiest lane
+// (profiles/r2_e_lj_queued.txt: 9 of 32 lanes active).
+// The order of the additions is the reference's: site-pair energies of one shape pair in iproduct
+// order, shape-pair energies in sequence order, each by one lane, one after the other.  Terms that
+// are skipped are exactly +0.0 and neither a shape-pair energy nor the sum can be -0.0 (both start
+// at +0.0, and x + (-x) = +0.0), so skipping them - or adding a +0.0 - leaves every bit as it is.
+struct LjSweep {
+    float af, bxf, byf;  // lattice vectors a = (af, 0), b = (bxf, byf)
+    float wide, wide2;   // reach + 2 E and its square, E = bound of the single-precision displacement error
+    float ec;            // bound of the error of a single-precision site-pair displacement component
+};
+__device__ __forceinline__ LjSweep lj_sweep_setup(const KProblem &P, const Dof &d, const Trig &t) {
+    LjSweep s;
+    const double b = d.v[0] * d.v[1];
+    s.af = (float)d.v[0];
+    s.bxf = (float)(b * t.ca);
+    s.byf = (float)(b * t.sa);
+    // |v| <= |d0| + 3 |a| + 3 |b| <= 4 S with S = |a|_1 + |b|_1 (fractional positions are wrapped into
+    // [-0.5, 0.5)); the conversions of d0, a, b and the two chained fmas of a component add up to
+    // less than 2^-20 S; E = 2^-18 S leaves a factor four
+    const float S = s.af + fabsf(s.bxf) + fabsf(s.byf);
+    const float E = 3.814697265625e-06f * S;
+    s.wide = (float)P.lj_reach * (1.0f + 1e-6f) + 2.0f * E;
+    s.wide2 = s.wide * s.wide * (1.0f + 1e-6f);
+    // site pair: the two converted site positions (2^-24 R each), the sum B + D and the difference
+    // (2^-24 (4 S + 2 R) each) on top of E: below 2^-17 (S + R)
+    s.ec = 7.62939453125e-06f * (S + (float)P.lj_reach);
+    return s;
+}
+// bit (ix + 3) * 7 + (iy + 3) = image (ix, iy) of three shells, the zero offset left out
+// (cell.rs:216-225 with zero = false), in the order periodic_images yields them.  A row of images
+// (fixed iy) whose |dy| alone exceeds the reach is skipped as a whole.
+constexpr int kLjCentre = 24;
+template <bool SELF>
+__device__ __forceinline__ unsigned long long lj_sweep_pair(const LjSweep &s, float d0x, float d0y) {
+    unsigned long long m = 0ull;
+#pragma unroll
+    for (int iy = SELF ? 0 : -3; iy <= 3; ++iy) {
+        const float vy = fmaf((float)iy, s.byf, d0y);
+        if (fabsf(vy) <= s.wide) {
+            const float x0 = fmaf((float)iy, s.bxf, d0x), vy2 = vy * vy;
+#pragma unroll
+            for (int ix = (SELF && iy == 0) ? 1 : -3; ix <= 3; ++ix) {
+                if (ix == 0 && iy == 0) continue;
+                const float vx = fmaf((float)ix, s.af, x0);
+                const float d2 = fmaf(vx, vx, vy2);
+                if (d2 <= s.wide2) m |= 1ull << ((ix + 3) * 7 + (iy + 3));
+            }
+        }
+    }
+    if (SELF) m |= __brevll(m) >> 15;  // image -t of a shape around itself is as far as image t
+    return m;
+}
+
+// one queued site pair with the reference's expressions: site k of shape i in its cell placement
+// against site l of image (ix, iy) of shape j; g = the OWNER's column.
+// item: first << 14 | i << 12 | j << 10 | bit << 4 | k << 2 | l
+template <int NI, class Geo>
+__device__ __forceinline__ double lj_item_energy(const KProblem &P, Geo g, unsigned item) {
+    const int n = NI > 0 ? NI : P.n_items;
+    const int i = (item >> 12) & 3, j = (item >> 10) & 3, qb = (item >> 4) & 63, k = (item >> 2) & 3, l = item & 3;
+    const int cix = (qb * 37) >> 8;  // qb / 7 for qb < 49
+    const double dix = (double)(cix - 3), diy = (double)(qb - cix * 7 - 3);
+    const double a = g.ld(0), b = g.ld(1), ca = g.ld(2), sa = g.ld(3);
+    const double fx = g.ld(4 + j * 4 + 0) + dix, fy = g.ld(4 + j * 4 + 1) + diy;  // to_cartesian_translate (cell.rs:241-245)
+    const double yb = fy * b;
+    // the zero offset (an in-cell pair) gives shape j's own Cartesian position bit for bit (x + 0.0 == x)
+    const double X = fx * a + yb * ca, Y = yb * sa;
+    const int ei = g.comp0 + (i * n + k) * 2, ej = g.comp0 + (j * n + l) * 2;
+    const double sx = g.ld(ei + 0) + g.ld(4 + i * 4 + 2), sy = g.ld(ei + 1) + g.ld(4 + i * 4 + 3);
+    const double ox = g.ld(ej + 0) + X, oy = g.ld(ej + 1) + Y;
+    const double *it = P.items[k];
+    return lj_pair(sx - ox, sy - oy, it[2], it[3], it[4], P.lj_shift[k]);
+}
+
+// the single-precision pre-filter of one candidate image: bit k * n + l set when site k of shape i
+// may be within its cutoff of site l of image qb of shape j; g = the OWNER's column
+template <int NI, class Geo>
+__device__ __forceinline__ unsigned lj_prefilter(const KProblem &P, Geo g, int N, int i, int j, int qb) {
+    constexpr int NN = NI > 0 ? NI : kLjQueueSites;
+    const int n = NI > 0 ? NI : P.n_items, total = N * n;
+    const float2 p0 = *g.fpar(total, N, 0), p1 = *g.fpar(total, N, 1);  // (af, bxf), (byf, ec)
+    const float d0x = (float)(g.ld(4 + j * 4 + 2) - g.ld(4 + i * 4 + 2));
+    const float d0y = (float)(g.ld(4 + j * 4 + 3) - g.ld(4 + i * 4 + 3));
+    const int cix = (qb * 37) >> 8;
+    const float fix = (float)(cix - 3), fiy = (float)(qb - cix * 7 - 3);
+    const float Dx = fmaf(fix, p0.x, fmaf(fiy, p0.y, d0x)), Dy = fmaf(fiy, p1.x, d0y);
+    float bx[NN], by[NN];
+#pragma unroll
+    for (int l = 0; l < NN; ++l) {
+        const float2 B = g.ldf(total, j * n + (l < n ? l : 0));
+        bx[l] = B.x + Dx;
+        by[l] = B.y + Dy;
+    }
+    unsigned m = 0u;
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+        // true |d| < cutoff implies |d_f| < cutoff + 1.5 ec and r2_f <= (cutoff + 2 ec)^2
+        const double cut = P.items[k < n ? k : 0][4];
+        const float c = (float)cut * (1.0f + 1e-6f) + 2.0f * p1.y;
+        const float lim = cut == cut ? c * c * (1.0f + 1e-6f) : 3.0e38f;
+        const float2 A = g.ldf(total, i * n + (k < n ? k : 0));
+#pragma unroll
+        for (int l = 0; l < NN; ++l) {
+            const float dx = A.x - bx[l], dy = A.y - by[l];
+            const float r2 = fmaf(dx, dx, dy * dy);
+            if ((NI > 0 || (k < n && l < n)) && r2 <= lim) m |= 1u << (k * n + l);
+        }
+    }
+    return m;
+}
+
+// word w of a replica's candidate sequence: the in-cell pairs i < j (one candidate each, never
+// pruned: potential.rs:88-96), then every ordered (i, j) with the images in reach
+template <class Geo>
+__device__ __forceinline__ unsigned long long lj_word(Geo g, int N, int total, int w, int &i, int &j) {
+    const int PW = N * (N - 1) / 2;
+    if (w < PW) {
+        i = 0;
+        int r = w;
+        while (r >= N - 1 - i) {
+            r -= N - 1 - i;
+            ++i;
+        }
+        j = i + 1 + r;
+        return 1ull << kLjCentre;
+    }
+    const int x = w - PW;
+    i = N == 4 ? x >> 2 : (N == 2 ? x >> 1 : (N == 1 ? x : x / N));
+    j = x - i * N;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const unsigned long long m = *g.mask(total, i == j ? PW : lo * N - lo * (lo + 1) / 2 + (hi - lo - 1));
+    return i > j ? __brevll(m) >> 15 : m;  // bit q <-> bit 48 - q
+}
+
+// each lane that wants to contribute `want` entries gets its share of the 32 pool slots; returns how
+// many it may write (take), where (slot) and the number of entries of the whole warp (total)
+__device__ __forceinline__ void lj_pool_quota(int want, int &take, int &slot, int &total) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wanting = __ballot_sync(0xffffffffu, want > 0);
+    const int nw = __popc(wanting);
+    const int quota = (int)(__fdividef(32.0f, (float)(nw ? nw : 1)) + 0.01f);  // 32 / nw (exact where it is an integer)
+    const int rank = __popc(wanting & ((1u << lane) - 1u));
+    const int share = quota + (rank < 32 - quota * nw ? 1 : 0);
+    take = want < share ? want : share;
+    int incl = take;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += up;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    slot = incl - take;
+}
+
+// Warp-collective: all 32 lanes call it converged; lanes without a state to score pass live = false
+// and work on the others' entries.
+template <int NI>
+__device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, const Dof &d, const Trig &t, bool live) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int N = P.n_syms, n = NI > 0 ? NI : P.n_items, total = N * n;
+    const int PW = N * (N - 1) / 2;
+    unsigned *const pool = g.pool_entries(P.n_items, N);
+    double *const E = g.pool_energies(P.n_items, N);
+    // 1. image masks
+    int cands = 0;  // candidates this lane still has to hand out
+    if (live) {
+        const LjSweep S = lj_sweep_setup(P, d, t);
+        *g.fpar(total, N, 0) = make_float2(S.af, S.bxf);
+        *g.fpar(total, N, 1) = make_float2(S.byf, S.ec);
+        int m = 0;
+        for (int i = 0; i < N; ++i)
+            for (int j = i + 1; j < N; ++j, ++m) {
+                const float d0x = (float)(g.ld(4 + j * 4 + 2) - g.ld(4 + i * 4 + 2));
+                const float d0y = (float)(g.ld(4 + j * 4 + 3) - g.ld(4 + i * 4 + 3));
+                const unsigned long long bits = lj_sweep_pair<false>(S, d0x, d0y);
+                *g.mask(total, m) = bits;
+                cands += 2 * __popcll(bits);  // (i, j) and its mirror (j, i)
+            }
+        const unsigned long long self = lj_sweep_pair<true>(S, 0.0f, 0.0f);
+        *g.mask(total, PW) = self;
+        cands += N * __popcll(self) + PW;  // + the in-cell pairs (potential.rs:88-96), never pruned
+    }
+    int w = -1, i = 0, j = 0;
+    unsigned long long bits = 0ull;
+    double sum = 0.;
+    __syncwarp();
+    for (;;) {
+        int take, slot, entries;
+        lj_pool_quota(cands, take, slot, entries);
+        if (entries == 0) break;
+        // 2. this lane's next `take` candidates, in sequence order
+        for (int c = 0; c < take; ++c) {
+            while (bits == 0ull) bits = lj_word(g, N, total, ++w, i, j);
+            const int qb = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            pool[slot + c] = (lane << 16) | (unsigned)(i << 12) | (unsigned)(j << 10) | (unsigned)(qb << 4);
+        }
+        cands -= take;
+        __syncwarp();
+        if ((int)lane < entries) {  // one entry per lane: the energy of that shape pair
+            const unsigned en = pool[lane];
+            const TGeo G = g.of(en >> 16);
+            unsigned m = lj_prefilter<NI>(P, G, N, (en >> 12) & 3, (en >> 10) & 3, (en >> 4) & 63);
+            double e = 0.;
+            while (m) {
+                const int p = __ffs((int)m) - 1;
+                m &= m - 1;
+                const int k = (p * (n == 3 ? 86 : (n == 4 ? 64 : (n == 2 ? 128 : 256)))) >> 8;  // p / n
+                e += lj_item_energy<NI>(P, G, (en & 0x3ff0u) | (unsigned)(k << 2) | (unsigned)(p - k * n));
+            }
+            E[lane] = e;
+        }
+        __syncwarp();
+        // 3. the owner's sum, one shape pair after the other
+        for (int c = 0; c < take; ++c) sum += E[slot + c];
+        __syncwarp();
+    }
+    return -sum / (double)N;
+}
+
+// PotentialState::score (state/potential.rs:82-115) for one replica in one thread.  Warp-collective:
+// called by all 32 lanes converged; the result of a lane with live = false is meaningless.
+template <int NI>
+__device__ __forceinline__ double t_lj_score(const KProblem &P, TGeo g, const Dof &d, const Trig &t,
+                                             const CellCache &cc, bool live) {
+    if (live) lj_build_geometry<NI>(P, g, d, t);
+    // a site without cutoff: every image and every site pair contributes, the plain loops are dense
+    const bool plain = !(P.lj_reach < 1e300) || (NI > kLjQueueSites) || (NI == 0 && P.n_items > kLjQueueSites);
+    if (plain) return live ? t_lj_score_plain<NI>(P, g, d, t) : 0.;
+    if constexpr (NI > 0 && NI <= kLjQueueSites)
+        return t_lj_score_pooled<NI>(P, g, d, t, live);
+    else if constexpr (NI == 0)
+        return t_lj_score_pooled<0>(P, g, d, t, live);
+    else
+        return 0.;
 }
 
 #endif  // CP_THREAD_LJ_CUH

@@ -103,6 +103,26 @@ class Engine {
     cp_ctx *ctx_ = nullptr;
 };
 
+// ---- a list of GPUs behind one handle (cp_multi): the replica loop of analyse_state sharded over them
+class MultiEngine {
+  public:
+    explicit MultiEngine(const std::vector<int> &devices) {
+        check(cp_init_multi(devices.data(), static_cast<int>(devices.size()), &m_));
+    }
+    ~MultiEngine() { cp_multi_destroy(m_); }
+    MultiEngine(const MultiEngine &) = delete;
+    MultiEngine &operator=(const MultiEngine &) = delete;
+    cp_multi *raw() const { return m_; }
+    int devices() const {
+        int n = 0;
+        check(cp_multi_device_count(m_, &n));
+        return n;
+    }
+
+  private:
+    cp_multi *m_ = nullptr;
+};
+
 // ---- State (traits.rs:71-87): PackedState<S> and PotentialState<S> share this shape
 struct State {
     cp_problem problem{};
@@ -205,6 +225,24 @@ S monte_carlo_best_packing(S state, const BuildOptimiser &opts, std::uint64_t re
     if (details) d.replicas.resize(replications);
     check(cp_run(e.raw(), &state.problem, stages, 3, rng_mode, 0, replica_begin, replications, nullptr, &d.best,
                  details ? d.replicas.data() : nullptr));
+    if (std::isnan(d.best.result.score)) throw Error(CP_ERR_INVALID_STATE, "Error in running optimisation.");
+    for (int i = 0; i < CP_MAX_DOF; ++i) state.problem.dof[i] = d.best.result.dof[i];
+    return state;
+}
+
+// the same over several GPUs: replicas are sharded contiguously, the answer is the single-GPU one
+template <class S>
+S monte_carlo_best_packing(S state, const BuildOptimiser &opts, std::uint64_t replications, const MultiEngine &e,
+                           int rng_mode = CP_RNG_PCG64MCG, BestPacking *details = nullptr,
+                           std::uint64_t replica_begin = 0) {
+    cp_build_optimiser b = opts.raw();
+    cp_schedule stages[3];
+    check(cp_pipeline_schedules(&b, stages));
+    BestPacking local;
+    BestPacking &d = details ? *details : local;
+    if (details) d.replicas.resize(replications);
+    check(cp_multi_run(e.raw(), &state.problem, stages, 3, rng_mode, 0, replica_begin, replications, nullptr, &d.best,
+                       details ? d.replicas.data() : nullptr));
     if (std::isnan(d.best.result.score)) throw Error(CP_ERR_INVALID_STATE, "Error in running optimisation.");
     for (int i = 0; i < CP_MAX_DOF; ++i) state.problem.dof[i] = d.best.result.dof[i];
     return state;

@@ -45,3 +45,21 @@ def test_cpp_host_packing_improves(tmp_path):
     idx, best, _, _ = orc.analyse_state(ostate, orc.build_optimiser(steps=300, inner_steps=100, kt_finish=0.001), 0, 32, 4)
     bl = [l for l in out.stdout.splitlines() if l.startswith("best")][0].split()
     assert float(bl[1]) == best.score and int(bl[3]) == idx
+
+
+@pytest.mark.gpu
+def test_cpp_multi_gpu_same_answer(tmp_path):
+    """cp_init_multi / cp_multi_run (the replica loop of main.rs:221-253 sharded over a device list)
+    gives the single-context answer: best state, replica index and every replica's result, for all
+    three state types.  On a one-GPU box the list is (0, 0): two contexts, two streams; with more
+    GPUs every device takes a shard."""
+    import torch
+
+    n = torch.cuda.device_count()
+    ids = [str(k) for k in range(n)] if n > 1 else ["0", "0"]
+    out = subprocess.run([build(tmp_path), "multi", *ids], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("multi")]
+    assert len(lines) == 3 and all(l.endswith("same") for l in lines), out.stdout
+    last = [l for l in out.stdout.splitlines() if l.startswith("last shard")][0].split()
+    assert int(last[2]) + int(last[3].lstrip("+")) == 5 + 97

@@ -575,3 +575,46 @@ def test_philox_statistically_equivalent(eng):
     assert sum(a) / n == pytest.approx(sum(b) / n, rel=0.01)
     ra, rb = sum(r.rejections for r in res) / n, sum(r.rejections for r in ores) / n
     assert ra == pytest.approx(rb, rel=0.02)
+
+
+# ------------------------------------------------------------------ several GPUs behind one handle
+def test_multi_engine_matches_single_context(eng):
+    """cp_init_multi / cp_multi_run: the replicas of analyse_state's loop (main.rs:221-253) sharded
+    over a device list.  Seeds are global replica ids, so the result equals the one-context run and
+    the oracle's, whatever the list - here every visible GPU, or the same GPU three times."""
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0, 0]
+    multi = cp.MultiEngine(devices)
+    try:
+        for spec, group in ((("polygon", 5), "p2"), (("trimer",), "p2gg"), (("lj_trimer",), "p2")):
+            cstate, ostate = make_states(spec, group)
+            bopt = orc.build_optimiser(steps=200, inner_steps=100)
+            n, begin = 101, 7
+            best, res = cp.monte_carlo_best_packing(cstate, c_build(bopt), n, engine=multi, replica_begin=begin,
+                                                    return_all=True)
+            best1, res1 = cp.monte_carlo_best_packing(cstate, c_build(bopt), n, engine=eng, replica_begin=begin,
+                                                      return_all=True)
+            assert [(list(r.dof), r.score, r.rejections, r.moves) for r in res] == \
+                   [(list(r.dof), r.score, r.rejections, r.moves) for r in res1]
+            assert (best.best_replica, best.best_score, best.dof) == (best1.best_replica, best1.best_score, best1.dof)
+            idx, obest, ores, _ = orc.analyse_state(ostate, bopt, begin, n, n_threads=4)
+            assert best.best_replica == begin + idx and best.best_score == obest.score
+            shards = multi.shards()
+            assert [s[0] for s in shards][0] == begin and sum(s[1] for s in shards) == n
+            assert max(s[1] for s in shards) - min(s[1] for s in shards) <= 1
+        # fewer replicas than devices: the empty shards are skipped
+        cstate, _ = make_states(("polygon", 4), "p1")
+        best, res = cp.monte_carlo_best_packing(cstate, cp.BuildOptimiser.cli_defaults(steps=100, inner_steps=100),
+                                                len(devices) - 1, engine=multi, return_all=True)
+        assert len(res) == len(devices) - 1 and best.best_score > 0
+    finally:
+        multi.close()
+
+
+def test_multi_engine_rejects_bad_lists():
+    with pytest.raises(cp.CrystalPackingError):
+        cp.MultiEngine([])
+    with pytest.raises(cp.CrystalPackingError):
+        cp.MultiEngine([0, 4096])

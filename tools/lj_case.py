@@ -1,5 +1,6 @@
 """One LJ workload for profiling: BASELINE.json configs[3], LJShape2::from_trimer in p2gg,
-131,072 replicas, 3-stage pipeline with 100 + 200 + 200 steps.  usage: python tools/lj_case.py"""
+131,072 replicas, 3-stage pipeline with 100 + steps + steps moves (default 200; the packings become
+dense - and a move expensive - after ~2,000).  usage: python tools/lj_case.py [steps] [replicas]"""
 import os
 import sys
 
@@ -9,8 +10,9 @@ import crystal_packing_b200 as cp  # noqa: E402
 
 eng = cp.Engine(0)
 state = cp.PotentialState.from_group(cp.LJShape2.from_trimer(0.637556, 120.0, 1.0), "p2gg")
-sched = cp.BuildOptimiser.cli_defaults(steps=200, inner_steps=200).pipeline()
-n = 131072
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+sched = cp.BuildOptimiser.cli_defaults(steps=steps, inner_steps=min(1000, steps)).pipeline()
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
 for _ in range(2):
     eng.prepare(state._problem, sched, n, rng=cp.RNG_PHILOX)
     eng.launch()

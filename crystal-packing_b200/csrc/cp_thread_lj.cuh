@@ -323,24 +323,15 @@ __device__ __forceinline__ unsigned lj_prefilter(const KProblem &P, Geo g, int N
     return m;
 }
 
-// word w of a replica's candidate sequence: the in-cell pairs i < j (one candidate each, never
-// pruned: potential.rs:88-96), then every ordered (i, j) with the images in reach
+// (i << 2) | j of in-cell pair p: pairs in the order (0,1),(0,2),..,(N-2,N-1) (potential.rs:88-96)
+__device__ __forceinline__ int lj_pair_of(int p, int N) {
+    const unsigned lut = N == 4 ? 0xB76321u : (N == 3 ? 0x621u : 0x1u);
+    return (int)((lut >> (4 * p)) & 15u);
+}
+// the image mask of the ordered pair (i, j): stored for i < j, mirrored for i > j, one for all i == j
 template <class Geo>
-__device__ __forceinline__ unsigned long long lj_word(Geo g, int N, int total, int w, int &i, int &j) {
+__device__ __forceinline__ unsigned long long lj_image_mask(Geo g, int N, int total, int i, int j) {
     const int PW = N * (N - 1) / 2;
-    if (w < PW) {
-        i = 0;
-        int r = w;
-        while (r >= N - 1 - i) {
-            r -= N - 1 - i;
-            ++i;
-        }
-        j = i + 1 + r;
-        return 1ull << kLjCentre;
-    }
-    const int x = w - PW;
-    i = N == 4 ? x >> 2 : (N == 2 ? x >> 1 : (N == 1 ? x : x / N));
-    j = x - i * N;
     const int lo = i < j ? i : j, hi = i < j ? j : i;
     const unsigned long long m = *g.mask(total, i == j ? PW : lo * N - lo * (lo + 1) / 2 + (hi - lo - 1));
     return i > j ? __brevll(m) >> 15 : m;  // bit q <-> bit 48 - q
@@ -375,8 +366,11 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
     const int PW = N * (N - 1) / 2;
     unsigned *const pool = g.pool_entries(P.n_items, N);
     double *const E = g.pool_energies(P.n_items, N);
-    // 1. image masks
-    int cands = 0;  // candidates this lane still has to hand out
+    // 1. image masks.  The in-cell pairs i < j (potential.rs:88-96) pass the same reach test: beyond it
+    // every site pair is outside its cutoff and the shape-pair energy is exactly +0.0.
+    int cands = 0;          // candidates this lane still has to hand out
+    unsigned incell = 0u;   // in-cell pairs within reach, bit = pair index
+    unsigned nonempty = 0u; // ordered pairs (i, j) with an image in reach, bit = i * N + j
     if (live) {
         const LjSweep S = lj_sweep_setup(P, d, t);
         *g.fpar(total, N, 0) = make_float2(S.af, S.bxf);
@@ -389,12 +383,19 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
                 const unsigned long long bits = lj_sweep_pair<false>(S, d0x, d0y);
                 *g.mask(total, m) = bits;
                 cands += 2 * __popcll(bits);  // (i, j) and its mirror (j, i)
+                if (bits) nonempty |= (1u << (i * N + j)) | (1u << (j * N + i));
+                if (fmaf(d0x, d0x, d0y * d0y) <= S.wide2) {
+                    incell |= 1u << m;
+                    ++cands;
+                }
             }
         const unsigned long long self = lj_sweep_pair<true>(S, 0.0f, 0.0f);
         *g.mask(total, PW) = self;
-        cands += N * __popcll(self) + PW;  // + the in-cell pairs (potential.rs:88-96), never pruned
+        cands += N * __popcll(self);
+        if (self)
+            for (int i = 0; i < N; ++i) nonempty |= 1u << (i * N + i);
     }
-    int w = -1, i = 0, j = 0;
+    int i = 0, j = 0;
     unsigned long long bits = 0ull;
     double sum = 0.;
     __syncwarp();
@@ -404,9 +405,25 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
         if (entries == 0) break;
         // 2. this lane's next `take` candidates, in sequence order
         for (int c = 0; c < take; ++c) {
-            while (bits == 0ull) bits = lj_word(g, N, total, ++w, i, j);
-            const int qb = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
+            int qb;
+            if (incell) {
+                const int p = __ffs((int)incell) - 1;
+                incell &= incell - 1u;
+                const int ij = lj_pair_of(p, N);
+                i = ij >> 2;
+                j = ij & 3;
+                qb = kLjCentre;
+            } else {
+                if (bits == 0ull) {
+                    const int w = __ffs((int)nonempty) - 1;
+                    nonempty &= nonempty - 1u;
+                    i = N == 4 ? w >> 2 : (N == 2 ? w >> 1 : (N == 1 ? w : w / N));
+                    j = w - i * N;
+                    bits = lj_image_mask(g, N, total, i, j);
+                }
+                qb = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+            }
             pool[slot + c] = (lane << 16) | (unsigned)(i << 12) | (unsigned)(j << 10) | (unsigned)(qb << 4);
         }
         cands -= take;

@@ -75,6 +75,11 @@ pub struct CpCtx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct CpMulti {
+    _private: [u8; 0],
+}
+
 extern "C" {
     pub fn cp_device_count(out: *mut c_int) -> c_int;
     pub fn cp_init(device: c_int, out: *mut *mut CpCtx) -> c_int;
@@ -98,4 +103,22 @@ extern "C" {
         out_all: *mut CpReplicaResult,
     ) -> c_int;
     pub fn cp_score(ctx: *mut CpCtx, problem: *const CpProblem, dof: *const f64, n: u64, out_scores: *mut f64) -> c_int;
+    pub fn cp_init_multi(device_ids: *const c_int, n_devices: c_int, out: *mut *mut CpMulti) -> c_int;
+    pub fn cp_multi_destroy(m: *mut CpMulti);
+    pub fn cp_multi_device_count(m: *const CpMulti, out: *mut c_int) -> c_int;
+    pub fn cp_multi_context(m: *mut CpMulti, k: c_int, out: *mut *mut CpCtx) -> c_int;
+    pub fn cp_multi_shard(m: *const CpMulti, k: c_int, replica_begin: *mut u64, n_replicas: *mut u64) -> c_int;
+    pub fn cp_multi_run(
+        m: *mut CpMulti,
+        problem: *const CpProblem,
+        stages: *const CpSchedule,
+        n_stages: c_int,
+        rng_mode: c_int,
+        seed_base: u64,
+        replica_begin: u64,
+        n_replicas: u64,
+        init_dof: *const f64,
+        out_best: *mut CpBest,
+        out_all: *mut CpReplicaResult,
+    ) -> c_int;
 }

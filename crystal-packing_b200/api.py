@@ -448,6 +448,24 @@ class _State:
 
         return state_from_json(text, cls, cls.shape_types)
 
+    def as_positions(self):
+        """State::as_positions (packed.rs:97-106, potential.rs:123-132); see render.py."""
+        from .render import as_positions
+
+        return as_positions(self)
+
+    def cartesian_positions(self):
+        """3x3 Cartesian transforms of the shapes in the cell (packed.rs:112-115)."""
+        from .render import cartesian_positions
+
+        return cartesian_positions(self)
+
+    def as_svg(self):
+        """ToSVG::as_svg (to_svg.rs:127-275) as the text svg::save writes (main.rs:266)."""
+        from .render import as_svg
+
+        return as_svg(self)
+
 
 class PackedState(_State):
     shape_types = (LineShape, MolecularShape2)

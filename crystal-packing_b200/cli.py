@@ -7,7 +7,7 @@ Same positional group, shape sub-commands (`polygon --sides`, `trimer -d -a -r`,
 `-p/--potential {LJ,Hard}`, `--replications`, `-s/--steps`, `--kt-start`, `--kt-finish`,
 `--kt-ratio`, `--max-step-size`, `--inner-steps`, `--convergence`, `--outfile`, `--start-config`
 (read here; the reference declares it and ignores it).  Writes `<outfile>.json` in the reference's
-serde layout.  The SVG the reference also writes is outside the scope of this engine.  Extra:
+serde layout and `<outfile>.svg` (main.rs:263-266; render.py).  Extra:
 `--rng {pcg,philox}` (pcg reproduces the reference's random stream) and `--device`.
 """
 import argparse
@@ -85,6 +85,8 @@ def main(argv=None):
     out = args.outfile[:-5] if args.outfile.endswith(".json") else args.outfile
     with open(out + ".json", "w") as f:
         f.write(best.to_json())
+    with open(out + ".svg", "w") as f:  # svg::save(outfile.with_extension("svg"), ..) (main.rs:266)
+        f.write(best.as_svg())
     return 0
 
 

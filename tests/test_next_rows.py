@@ -90,6 +90,8 @@ def test_cli_end_to_end(tmp_path):
                         "trimer"], capture_output=True, text=True, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr
     assert json.loads(open(str(out) + ".json").read())["shape"]["name"] == "Trimer"
+    svg = open(str(out) + ".svg").read()  # main.rs:266
+    assert svg.startswith("<svg ") and svg.count("<use ") == 9 + 9 * 2 and svg.count("<circle ") == 3
     out2 = tmp_path / "pent"
     r = subprocess.run([sys.executable, "-m", "crystal_packing_b200.cli", "p2", "-s", "600", "--inner-steps", "200",
                         "--replications", "16", "--outfile", str(out2), "polygon", "--sides", "5"],

@@ -265,27 +265,6 @@ __device__ __forceinline__ unsigned long long lj_sweep_pair(const LjSweep &s, fl
     return m;
 }
 
-// one queued site pair with the reference's expressions: site k of shape i in its cell placement
-// against site l of image (ix, iy) of shape j; g = the OWNER's column.
-// item: first << 14 | i << 12 | j << 10 | bit << 4 | k << 2 | l
-template <int NI, class Geo>
-__device__ __forceinline__ double lj_item_energy(const KProblem &P, Geo g, unsigned item) {
-    const int n = NI > 0 ? NI : P.n_items;
-    const int i = (item >> 12) & 3, j = (item >> 10) & 3, qb = (item >> 4) & 63, k = (item >> 2) & 3, l = item & 3;
-    const int cix = (qb * 37) >> 8;  // qb / 7 for qb < 49
-    const double dix = (double)(cix - 3), diy = (double)(qb - cix * 7 - 3);
-    const double a = g.ld(0), b = g.ld(1), ca = g.ld(2), sa = g.ld(3);
-    const double fx = g.ld(4 + j * 4 + 0) + dix, fy = g.ld(4 + j * 4 + 1) + diy;  // to_cartesian_translate (cell.rs:241-245)
-    const double yb = fy * b;
-    // the zero offset (an in-cell pair) gives shape j's own Cartesian position bit for bit (x + 0.0 == x)
-    const double X = fx * a + yb * ca, Y = yb * sa;
-    const int ei = g.comp0 + (i * n + k) * 2, ej = g.comp0 + (j * n + l) * 2;
-    const double sx = g.ld(ei + 0) + g.ld(4 + i * 4 + 2), sy = g.ld(ei + 1) + g.ld(4 + i * 4 + 3);
-    const double ox = g.ld(ej + 0) + X, oy = g.ld(ej + 1) + Y;
-    const double *it = P.items[k];
-    return lj_pair(sx - ox, sy - oy, it[2], it[3], it[4], P.lj_shift[k]);
-}
-
 // the single-precision pre-filter of one candidate image: bit k * n + l set when site k of shape i
 // may be within its cutoff of site l of image qb of shape j; g = the OWNER's column
 template <int NI, class Geo>
@@ -431,13 +410,29 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
         if ((int)lane < entries) {  // one entry per lane: the energy of that shape pair
             const unsigned en = pool[lane];
             const TGeo G = g.of(en >> 16);
-            unsigned m = lj_prefilter<NI>(P, G, N, (en >> 12) & 3, (en >> 10) & 3, (en >> 4) & 63);
+            const int ei = (en >> 12) & 3, ej = (en >> 10) & 3, qb = (en >> 4) & 63;
+            unsigned m = lj_prefilter<NI>(P, G, N, ei, ej, qb);
             double e = 0.;
-            while (m) {
-                const int p = __ffs((int)m) - 1;
-                m &= m - 1;
-                const int k = (p * (n == 3 ? 86 : (n == 4 ? 64 : (n == 2 ? 128 : 256)))) >> 8;  // p / n
-                e += lj_item_energy<NI>(P, G, (en & 0x3ff0u) | (unsigned)(k << 2) | (unsigned)(p - k * n));
+            if (m) {
+                // the displacement of the image (to_cartesian_translate, cell.rs:241-245), once per entry;
+                // the zero offset of an in-cell pair gives shape j's own position bit for bit (x + 0.0 == x)
+                const int cix = (qb * 37) >> 8;  // qb / 7 for qb < 49
+                const double dix = (double)(cix - 3), diy = (double)(qb - cix * 7 - 3);
+                const double fx = G.ld(4 + ej * 4 + 0) + dix, fy = G.ld(4 + ej * 4 + 1) + diy;
+                const double yb = fy * G.ld(1);
+                const double X = fx * G.ld(0) + yb * G.ld(2), Y = yb * G.ld(3);
+                const double cxi = G.ld(4 + ei * 4 + 2), cyi = G.ld(4 + ei * 4 + 3);
+                const int bi = G.comp0 + ei * n * 2, bj = G.comp0 + ej * n * 2;
+                do {  // the surviving site pairs in iproduct order (lj_shape.rs:35-39), LJ2::energy in f64
+                    const int p = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const int k = (p * (n == 3 ? 86 : (n == 4 ? 64 : (n == 2 ? 128 : 256)))) >> 8;  // p / n
+                    const int l = p - k * n;
+                    const double sx = G.ld(bi + k * 2 + 0) + cxi, sy = G.ld(bi + k * 2 + 1) + cyi;
+                    const double ox = G.ld(bj + l * 2 + 0) + X, oy = G.ld(bj + l * 2 + 1) + Y;
+                    const double *pk = P.items[k];
+                    e += lj_pair(sx - ox, sy - oy, pk[2], pk[3], pk[4], P.lj_shift[k]);
+                } while (m);
             }
             E[lane] = e;
         }

@@ -10,11 +10,18 @@
  * x86-64 and on sm_100a, so host and device produce identical bits provided the compilers do not
  * contract or reassociate (host: -ffp-contract=off, device: -fmad=false).
  *
- * Accuracy (measured in tests/test_cp_math.py against mpmath and glibc): < 1 ulp, and equal to
- * glibc for the overwhelming majority of arguments in the DOF ranges ([0, 2pi], [pi/4, pi/2]).
+ * Accuracy (tests/test_oracle_known_answers.py::test_math_modes_agree_closely, against glibc):
+ * within 1 ulp, and equal to glibc for the overwhelming majority of arguments in the DOF ranges
+ * ([0, 2pi], [pi/4, pi/2]).
  *
- * The polynomial coefficients and the split constants of pi/2 and ln2 are the classic Sun fdlibm
- * numeric constants (public, freely redistributable); the code arrangement is ours.
+ * The polynomial coefficients and the split constants of pi/2 and ln2 are the numeric constants of
+ * Sun's fdlibm (k_sin.c, k_cos.c, e_exp.c, e_rem_pio2.c); the code arrangement is ours.  fdlibm's
+ * notice, which covers those constants:
+ *
+ *   Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+ *   Developed at SunSoft, a Sun Microsystems, Inc. business.
+ *   Permission to use, copy, modify, and distribute this software is freely granted,
+ *   provided that this notice is preserved.
  */
 #ifndef CP_MATH_H
 #define CP_MATH_H

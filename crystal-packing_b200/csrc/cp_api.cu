@@ -158,6 +158,26 @@ static cp_status make_kproblem(const cp_problem *p, KProblem *k) {
         k->symsf[s][2] = (float)p->syms[s][3];
         k->symsf[s][3] = (float)p->syms[s][4];
     }
+    // Signed images: the rotation part of every operator is that of operator 0 with the signs of its
+    // rows flipped (identity, two-fold axis, mirrors: all seven plane groups of the reference).  Then
+    // the rotated shape points of image s are those of image 0 with the same sign flips, bit for bit
+    // (cp_thread.cuh: t_place evaluates fmaf(+-x, c, +-y * s)), and one set serves all images.
+    k->signed_images = 1;
+    for (int s = 0; s < p->n_syms; ++s) {
+        bool found = false;
+        for (int a = 0; a < 4 && !found; ++a) {
+            const float ax = (a & 1) ? -1.0f : 1.0f, ay = (a & 2) ? -1.0f : 1.0f;
+            if (k->symsf[s][0] == ax * k->symsf[0][0] && k->symsf[s][1] == ax * k->symsf[0][1] &&
+                k->symsf[s][2] == ay * k->symsf[0][2] && k->symsf[s][3] == ay * k->symsf[0][3]) {
+                k->sgnf[s][0] = ax;
+                k->sgnf[s][1] = ay;
+                found = true;
+            }
+        }
+        if (!found) k->signed_images = 0;
+    }
+    if (!k->signed_images)
+        for (int s = 0; s < CP_MAX_SYMS; ++s) k->sgnf[s][0] = k->sgnf[s][1] = 1.0f;
     k->radf = (float)p->enclosing_radius;
     k->chain = 0;
     if (p->kind == CP_POLYGON) {

@@ -35,6 +35,9 @@ struct KProblem {
     double lj_reach;  // max cutoff + 2 * max |site position|; +inf when a site has no cutoff
     // single-precision copies for the certificates of the one-thread-per-replica kernels (cp_filter.h)
     float symsf[CP_MAX_SYMS][4];        // rotation part of the operators: S[0], S[1], S[3], S[4]
+    float sgnf[CP_MAX_SYMS][2];         // signed_images: row signs of operator s relative to operator 0
+    int signed_images;                  // every rotation part = operator 0's with the signs of its rows
+                                        // flipped (+-1, exact): one set of rotated points serves all images
     float ptsf[2 * CP_MAX_ITEMS][2];    // polygon chain: the n start points; other polygons: start, end
                                         // of every segment; discs: the centres
     float discrf[CP_MAX_ITEMS];         // disc radii

@@ -15,10 +15,10 @@ int cp_thread_route_ni(const KProblem &P) {
 }
 
 size_t cp_thread_shared_bytes(const KProblem &P) {
-    if (P.kind == CP_LJ) return thread_block_shared_bytes<CP_LJ, 0, 0>(P.n_items, P.n_syms);
+    if (P.kind == CP_LJ) return thread_block_shared_bytes<CP_LJ, 0, 0>(P);
     if (P.kind == CP_POLYGON && cp_thread_route_ni(P) == 0)
-        return thread_block_shared_bytes<CP_POLYGON, 0, 0>(P.n_items, P.n_syms);
-    return thread_block_shared_bytes<CP_DISCS, 0, 0>(P.n_items, P.n_syms);  // one point per component
+        return thread_block_shared_bytes<CP_POLYGON, 0, 0>(P);
+    return thread_block_shared_bytes<CP_DISCS, 0, 0>(P);  // one point per component
 }
 
 bool cp_thread_kernel_fits(const KProblem &P) { return cp_thread_shared_bytes(P) <= 200 * 1024; }

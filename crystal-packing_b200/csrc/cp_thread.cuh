@@ -24,6 +24,8 @@
 #ifndef CP_THREAD_CUH
 #define CP_THREAD_CUH
 
+#include <type_traits>
+
 #include "cp_device.cuh"
 #include "cp_filter.h"
 #include "cp_thread_lj.cuh"
@@ -36,7 +38,9 @@ constexpr int kQueueCap = 96;  // component pairs waiting for their f64 evaluati
 // stands for the in-cell pair i < j, whose displacement to_cartesian(f_j + (0, 0)) is bit for bit
 // j's own Cartesian position (x + 0.0 == x), so one routine serves both kinds.
 constexpr int kCentreBit = 24;
-// slow schedule variables in the f64 plane, relative to dof0() + 16 (raw bits for the integers)
+// the replica's state between moves in the f64 plane, relative to dof0()
+enum { kStUpper = 6, kStTrig = 8, kStSched = 12, kStElems = 18 };
+// slow schedule variables, relative to dof0() + kStSched (raw bits for the integers)
 enum { kSchedScoreStart = 0, kSchedStepRatio, kSchedRejections, kSchedMoves, kSchedLoopsLeft, kSchedStage };
 // decodes a candidate bit into its image offsets
 __device__ __forceinline__ void image_of_bit(int q, int &ix, int &iy) {
@@ -52,23 +56,33 @@ __device__ __forceinline__ void image_of_bit(int q, int &ix, int &iy) {
 //               symmetry image s: 6 + 4s + {0 fx, 1 fy (wrapped fractional), 2 cx, 3 cy (Cartesian)},
 //               then (at dof0()) the replica's state between moves, so that the registers hold only
 //               what every draw needs: + 0..5 the six DOFs of the current (accepted) state (the draw
-//               loop reads "the DOF the RNG picked" with one indexed load), + 6..11 their upper
-//               bounds for this stage, + 12..15 sin, cos of the site angle and of the cell angle of
-//               that state, + 16..21 the schedule's slow variables (kSched*)
-//   f32 plane : per image s, per point p: x, y of the rotated point (relative to the image's centre);
-//               last element: the squared distance below which an image is a candidate for certain
+//               loop reads "the DOF the RNG picked" with one indexed load), + kStUpper.. the upper
+//               bounds of length and ratio for this stage (the other four are constants), + kStTrig..
+//               sin, cos of the site angle and of the cell angle of that state, + kStSched.. the
+//               schedule's slow variables (kSched*)
+//   f32 plane : per point p: x, y of the rotated point (relative to the image's centre) - of image 0
+//               only when every operator's rotation part is that of operator 0 up to the signs of
+//               its rows (KProblem::signed_images: all seven plane groups of the reference; the
+//               other images' points are those with their signs flipped, bit for bit), else of
+//               every image; last element: the squared distance below which an image is a candidate
+//               for certain
 //   masks     : N (N - 1) / 2 pair words + 1 self word (u64); in registers for multiplicities 1, 2
-//   constants : the shape components, the symmetry operators and the lower bounds of the DOFs (f64)
+//   constants : the shape components, the symmetry operators, the lower bounds of the DOFs and the
+//               upper bounds that do not depend on the stage (f64)
 template <int KIND, int NI, int NS>
 struct TLayout {
-    int n, N, NP;
-    __host__ __device__ TLayout(int n_items, int n_syms)
-        : n(NI > 0 ? NI : n_items), N(NS > 0 ? NS : n_syms), NP((KIND == CP_POLYGON && NI == 0) ? 2 * n : n) {}
-    __host__ __device__ int dof0() const { return 6 + 4 * N; }   // element of DOF 0; upper bounds follow at + 6
-    __host__ __device__ int f64_elems() const { return 28 + 4 * N; }
-    __host__ __device__ int f32_elems() const { return 2 * N * NP; }
+    // NF: images whose rotated points are stored.  Multiplicities 1 and 2 keep all of theirs (their
+    // footprint does not bound the occupancy, and the certificates save the sign multiplications).
+    int n, N, NP, NF;
+    __host__ __device__ TLayout(int n_items, int n_syms, int signed_images)
+        : n(NI > 0 ? NI : n_items), N(NS > 0 ? NS : n_syms), NP((KIND == CP_POLYGON && NI == 0) ? 2 * n : n),
+          NF((signed_images && NS != 1 && NS != 2) ? 1 : N) {}
+    __host__ __device__ TLayout(const KProblem &P) : TLayout(P.n_items, P.n_syms, P.signed_images) {}
+    __host__ __device__ int dof0() const { return 6 + 4 * N; }   // element of DOF 0 (kSt* follow)
+    __host__ __device__ int f64_elems() const { return 6 + 4 * N + kStElems; }
+    __host__ __device__ int f32_elems() const { return 2 * NF * NP; }
     __host__ __device__ int pairs() const { return N * (N - 1) / 2; }
-    __host__ __device__ int const_doubles() const { return n * 4 + N * 6 + 6; }
+    __host__ __device__ int const_doubles() const { return n * 4 + N * 6 + 12; }
     __host__ __device__ size_t bytes() const {
         return 8 * (size_t)(32 * f64_elems() + 32 * (pairs() + 1) + const_doubles()) + 4 * (size_t)(32 * (f32_elems() + 1)) +
                4 * (size_t)(72 + kQueueCap);
@@ -78,7 +92,7 @@ struct TLayout {
 struct TView {
     double *f64;                // plane base (lane 0)
     unsigned long long *masks;  // plane base
-    double *c_items, *c_syms, *c_lo;
+    double *c_items, *c_syms, *c_lo;  // c_lo[0..5] lower bounds, c_lo[6..11] stage-independent upper bounds
     float *f32;       // plane base
     unsigned *pool;   // [0..31] entries, [32..63] hit flag of each lane's replica, [64] queue fill
     unsigned *queue;  // kQueueCap items
@@ -86,14 +100,14 @@ struct TView {
 
 template <int KIND, int NI, int NS>
 __device__ __forceinline__ TView thread_view(double *smem, const KProblem &P) {
-    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    const TLayout<KIND, NI, NS> L(P);
     TView v;
     v.f64 = smem;
     v.masks = reinterpret_cast<unsigned long long *>(smem + 32 * L.f64_elems());
     v.c_items = smem + 32 * (L.f64_elems() + L.pairs() + 1);
     v.c_syms = v.c_items + L.n * 4;
     v.c_lo = v.c_syms + L.N * 6;
-    v.f32 = reinterpret_cast<float *>(v.c_lo + 6);
+    v.f32 = reinterpret_cast<float *>(v.c_lo + 12);
     v.pool = reinterpret_cast<unsigned *>(v.f32 + 32 * (L.f32_elems() + 1));
     v.queue = v.pool + 72;
     return v;
@@ -102,12 +116,14 @@ __device__ __forceinline__ TView thread_view(double *smem, const KProblem &P) {
 // block constants for the f64 evaluations (any lane, any component index)
 template <int KIND, int NI, int NS>
 __device__ __forceinline__ void thread_stage_constants(const TView &v, const KProblem &P) {
-    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    const TLayout<KIND, NI, NS> L(P);
     for (int e = threadIdx.x; e < L.n * 4; e += kThreadBlock) v.c_items[e] = P.items[e >> 2][e & 3];
     for (int e = threadIdx.x; e < L.N * 6; e += kThreadBlock) v.c_syms[e] = P.syms[e / 6][e % 6];
     if (threadIdx.x < 6) {  // lower bounds per slot (cell.rs:139-160, site.rs:69-88)
         const int e = threadIdx.x;
         v.c_lo[e] = e == 0 ? 0.01 : (e == 1 ? 0.1 : (e == 2 ? CP_PI / 4. : (e == 5 ? 0. : -0.5)));
+        // upper bounds; those of length and ratio are captured per stage and live in the lane's column
+        v.c_lo[6 + e] = e == 2 ? CP_PI / 2. : (e == 5 ? CP_TAU : 0.5);
     }
     __syncwarp();
 }
@@ -118,6 +134,15 @@ struct TPts {
     const float *rad;
     __device__ __forceinline__ float x(int k) const { return p[(2 * k) * 32]; }
     __device__ __forceinline__ float y(int k) const { return p[(2 * k + 1) * 32]; }
+    __device__ __forceinline__ float r(int k) const { return rad[k]; }
+};
+// the same with the signs of the image's rows applied (sx, sy = +-1: exact)
+struct TPtsSigned {
+    const float *p;
+    const float *rad;
+    float sx, sy;
+    __device__ __forceinline__ float x(int k) const { return sx * p[(2 * k) * 32]; }
+    __device__ __forceinline__ float y(int k) const { return sy * p[(2 * k + 1) * 32]; }
     __device__ __forceinline__ float r(int k) const { return rad[k]; }
 };
 
@@ -148,7 +173,7 @@ __device__ __forceinline__ void image_rotation(const double *S, double ct, doubl
 // in f64 with the reference's expressions; the rotated shape points in f32 for the certificates.
 template <int KIND, int NI, int NS>
 __device__ __forceinline__ void t_place(const KProblem &P, const TView &v, const Dof &d, const Trig &t) {
-    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    const TLayout<KIND, NI, NS> L(P);
     double *g = v.f64 + threadIdx.x;
     float *h = v.f32 + threadIdx.x;
     const double a = d.v[0], b = d.v[0] * d.v[1];
@@ -169,6 +194,7 @@ __device__ __forceinline__ void t_place(const KProblem &P, const TView &v, const
         g[(6 + 4 * s + 2) * 32] = cx;
         g[(6 + 4 * s + 3) * 32] = cy;
         // rotation block of the same product, single precision (certificates only)
+        if (s >= L.NF) continue;  // signed images: the points of image 0 serve every image
         const float *F = P.symsf[s];
         const float m00 = fmaf(F[0], ctf, F[1] * stf), m01 = fmaf(F[1], ctf, -(F[0] * stf));
         const float m10 = fmaf(F[2], ctf, F[3] * stf), m11 = fmaf(F[3], ctf, -(F[2] * stf));
@@ -233,7 +259,7 @@ __device__ __forceinline__ CpfSweep t_sweep_setup(const KProblem &P, const Dof &
 template <int KIND, int NI, int NS>
 __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const Dof &d, const Trig &t,
                                         const CellCache &cc, TCands<NS> &c) {
-    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    const TLayout<KIND, NI, NS> L(P);
     const double *g = v.f64 + threadIdx.x;
     const CpfSweep s = t_sweep_setup(P, d, t, cc);
     v.f32[L.f32_elems() * 32 + threadIdx.x] = s.narrow2;
@@ -413,7 +439,7 @@ __device__ __noinline__ void t_flush(const KProblem &P, const TView &v, int qcou
 // Must be called by all 32 lanes converged; lanes without a proposal pass remaining = 0.
 template <int KIND, int NI, int NS>
 __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v, TCands<NS> &c) {
-    const TLayout<KIND, NI, NS> L(P.n_items, P.n_syms);
+    const TLayout<KIND, NI, NS> L(P);
     constexpr int W = NI > 0 ? cpf_words(NI) : CPF_MAX_WORDS;
     const unsigned lane = threadIdx.x & 31u;
     const int NP2 = L.NP * 2, PW = L.pairs(), nn = L.n * L.n;
@@ -463,9 +489,32 @@ __device__ __forceinline__ bool t_overlap_warp(const KProblem &P, const TView &v
             const double a = o[0 * 32], b = o[1 * 32], ca = o[2 * 32], sa = o[3 * 32];
             const double fx = o[(6 + 4 * j + 0) * 32] + (double)ix, fy = o[(6 + 4 * j + 1) * 32] + (double)iy;
             const double yb = fy * b;
-            const float dX = (float)((fx * a + yb * ca) - o[(6 + 4 * i + 2) * 32]);
-            const float dY = (float)(yb * sa - o[(6 + 4 * i + 3) * 32]);
-            const TPts A{v.f32 + owner + (i * NP2) * 32, P.discrf}, B{v.f32 + owner + (j * NP2) * 32, P.discrf};
+            float dX = (float)((fx * a + yb * ca) - o[(6 + 4 * i + 2) * 32]);
+            float dY = (float)(yb * sa - o[(6 + 4 * i + 3) * 32]);
+            // Signed images: the stored points are image 0's; image s has them with the signs
+            // (sgnf[s]) of its rows, exactly.  The certificate is evaluated in shape i's frame with its
+            // signs undone: A's points as stored, B's with the product of the two sign pairs, delta
+            // with i's.  Flipping one coordinate of everything multiplies every cross product by -1
+            // exactly and leaves the squared distances as they are, and the certificate depends on the
+            // H pair and the G pair only through min |.| and the XOR of their signs (cp_filter.h):
+            // cmin, tau and the ambiguous set are bit for bit those of the flipped evaluation.
+            constexpr bool kAllStored = NS == 1 || NS == 2;
+            const int iA = L.NF == 1 ? 0 : i, iB = L.NF == 1 ? 0 : j;
+            const float sAx = kAllStored ? 1.0f : P.sgnf[i][0], sAy = kAllStored ? 1.0f : P.sgnf[i][1];
+            const TPts A{v.f32 + owner + (iA * NP2) * 32, P.discrf};
+            using PtsB = typename std::conditional<kAllStored, TPts, TPtsSigned>::type;
+            PtsB B;
+            if constexpr (kAllStored) {
+                B = TPts{v.f32 + owner + (iB * NP2) * 32, P.discrf};
+            } else {
+                const bool one = L.NF == 1;  // else every image is stored with its own signs
+                B = TPtsSigned{v.f32 + owner + (iB * NP2) * 32, P.discrf, one ? sAx * P.sgnf[j][0] : 1.0f,
+                               one ? sAy * P.sgnf[j][1] : 1.0f};
+                if (one) {
+                    dX *= sAx;
+                    dY *= sAy;
+                }
+            }
             // an image within rounding of the reference's 2R filter (or beyond it): candidacy itself is
             // in doubt, so no certificate is used and the f64 path applies the reference's own filter
             const bool force = q != kCentreBit && !(fmaf(dX, dX, dY * dY) <= v.f32[L.f32_elems() * 32 + owner]);
@@ -569,16 +618,16 @@ __device__ __forceinline__ double t_state_score(const KProblem &P, const TView &
 
 // shared memory of a block
 template <int KIND, int NI, int NS>
-__host__ __device__ inline size_t thread_block_shared_bytes(int n_items, int n_syms) {
-    if (KIND == CP_LJ) return lj_block_bytes(n_items, n_syms);
-    return TLayout<KIND, NI, NS>(n_items, n_syms).bytes();
+__host__ __device__ inline size_t thread_block_shared_bytes(const KProblem &P) {
+    if (KIND == CP_LJ) return lj_block_bytes(P.n_items, P.n_syms);
+    return TLayout<KIND, NI, NS>(P).bytes();
 }
 
-// Monte-Carlo optimisation, one replica per thread (see the header comment for the control flow):
-// MCOptimiser::optimise_state (optimisation.rs:80-180) for every stage, seeds and bounds per stage
-// as analyse_state / generate_basis set them.
-// Register budget = minimum resident blocks per SM: 14 warps per SM hold all 2,048 warps of a
-// 65,536-replica batch at once.
+// Monte-Carlo optimisation of the LJ potential, one replica per thread: MCOptimiser::optimise_state
+// (optimisation.rs:80-180) for every stage, seeds and bounds per stage as analyse_state /
+// generate_basis set them.  The replica's state lives in registers; the warp meets in t_lj_score.
+// Register budget = minimum resident blocks per SM (hard shapes: 14 warps per SM hold all 2,048
+// warps of a 65,536-replica batch at once).
 constexpr int thread_min_blocks(int kind, int ni) {
     return kind == CP_LJ ? 10 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)));
 }
@@ -589,16 +638,9 @@ constexpr int kDrawCap = 3;  // default; KParams::draw_cap
 template <int KIND, int NI, int NS, int RNG>
 __global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI))
 mc_thread_lj_kernel(const __grid_constant__ KParams K) {
+    static_assert(KIND == CP_LJ, "LJ only: hard shapes run mc_thread_kernel");
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
-    TView v{};
-    int e_dof = 0;
-    if constexpr (KIND != CP_LJ) {
-        v = thread_view<KIND, NI, NS>(smem, P);
-        thread_stage_constants<KIND, NI, NS>(v, P);
-        e_dof = TLayout<KIND, NI, NS>(P.n_items, P.n_syms).dof0();
-    }
-    double *const mine = v.f64 + threadIdx.x;  // this lane's column of the f64 plane (hard shapes)
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
     const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
     const unsigned long long replica = K.replica_begin + (active ? rep : 0ull);
@@ -614,15 +656,11 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
     }
     const int n_cell = n_cell_dof(P.family);
     const int n_basis = n_cell + 3;
-    const double area_n = P.area * (double)P.n_syms;  // numerator of packed.rs:84
     unsigned long long rejections = 0, moves = 0;
     double score_current = 0.;
 
     Rng rng;
     CellCache cc = cell_cache_of(d);
-    TCands<NS> cands;
-    if constexpr (KIND != CP_LJ) cands.sh = v.masks + threadIdx.x;
-    cands.tune = K.tune;
     // Every lane walks its own (stage, outer loop, inner step) schedule: replicas of one warp need
     // different numbers of scored proposals per inner loop (the in-bounds fraction depends on the
     // replica's cell), and synchronising at loop ends would leave the faster lanes idle there.  Only
@@ -637,13 +675,8 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
     auto begin_stage = [&]() {
         const KStage &S = K.stages[stage];
         // generate_basis(): bounds captured per optimise_state call (cell.rs:139-152)
-        if constexpr (KIND != CP_LJ) {
-            mine[(e_dof + 6 + 0) * 32] = d.v[0];
-            mine[(e_dof + 6 + 1) * 32] = d.v[1];
-        } else {
-            len0 = d.v[0];
-            ratio0 = d.v[1];
-        }
+        len0 = d.v[0];
+        ratio0 = d.v[1];
         rng_begin_stage<RNG>(rng, K.seed_base, replica, n_basis);
         kt = S.kt_start;
         step_ratio = 1.0;
@@ -666,14 +699,6 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
             if (loops_left > 0) return;
         }
     };
-    if constexpr (KIND != CP_LJ) {
-#pragma unroll
-        for (int i = 0; i < CP_MAX_DOF; ++i) mine[(e_dof + i) * 32] = d.v[i];
-        mine[(e_dof + 6 + 2) * 32] = CP_PI / 2.;  // the upper bounds that do not depend on the stage
-        mine[(e_dof + 6 + 3) * 32] = 0.5;
-        mine[(e_dof + 6 + 4) * 32] = 0.5;
-        mine[(e_dof + 6 + 5) * 32] = CP_TAU;
-    }
     // The first pass scores the initial state through the same code as every proposal
     // (optimisation.rs:81-84: an invalid initial state is an error); `first` is warp-uniform.
     bool first = true;
@@ -681,18 +706,11 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
         bool have = false;
         int slot = 6;  // 6 = no DOF changes (the first pass)
         double val = 0., new_val = 0., new_score = 0.;
-        unsigned long long threshold = 0ull;  // raw bits of draw #3
         if (first) {
             have = true;  // tail lanes score the template state too: their result is never written
         } else {
-            // Draw until a proposal needs scoring, at most kDrawCap draws per pass.  Out-of-bounds
+            // Draw until a proposal needs scoring, at most K.draw_cap draws per pass.  Out-of-bounds
             // proposals are rejected by Basis::set_value without a score (optimisation.rs:120-123).
-            // For hard shapes the packing fraction depends on the cell DOFs only, so
-            // `Some(new_score)` is known before any overlap test: when the Metropolis rule would
-            // reject even a valid state (a cell move that lowers the score, lost against the
-            // threshold) the reference's answer is "rejected" whether check_intersection says None or
-            // Some, and the overlap test is skipped.  Draw order (index, step, threshold) and every
-            // decision are unchanged.
             for (int draws = 0; draws < K.draw_cap && !done && !have; ++draws) {
                 if (it == inner) {  // end of an inner loop (optimisation.rs:138-167)
                     const KStage &S = K.stages[stage];
@@ -723,72 +741,20 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
                 rng_draw_move<RNG>(rng, basis_index, sample);
                 slot = basis_to_slot(basis_index, n_cell);
                 double lo, hi;
-                if constexpr (KIND != CP_LJ) {
-                    val = mine[(e_dof + slot) * 32];
-                    hi = mine[(e_dof + 6 + slot) * 32];
-                    lo = v.c_lo[slot];
-                } else {
-                    val = d.get(slot);
-                    slot_bounds(slot, len0, ratio0, lo, hi);
-                }
+                val = d.get(slot);
+                slot_bounds(slot, len0, ratio0, lo, hi);
                 new_val = val + step_scale * sample;
                 have = lo <= new_val && new_val <= hi;
-                if (!have) {
-                    ++loop_rejections;
-                    continue;
-                }
-                if constexpr (KIND != CP_LJ) {
-                    threshold = rng_draw_threshold_bits<RNG>(rng);
-                    new_score = score_current;  // site moves leave the packing fraction as it is
-                    if (slot <= 2) {
-                        double sa_new = t.sa;
-                        bool settled = false;
-                        if (slot == 2) {
-                            // Cell-angle move.  A single-precision sine (absolute error < 2^-21 on this
-                            // range; margin 4e-6) settles the two common outcomes without the f64
-                            // sine: the area shrinks by a relative 2e-6 or more, so new > old and the
-                            // move is accepted whatever the temperature (the exact sine and score are
-                            // taken in phase A); or it grows that much while kT is +0 (stages 1 and
-                            // 3), where exp(-inf) = 0 rejects, or while kT is so small that the exponent
-                            // underflows.  Everything else takes the exact path.
-                            const float s_old = (float)t.sa, s_new = __sinf((float)new_val);
-                            if (s_new < s_old * (1.0f - 4.0e-6f)) {
-                                settled = true;
-                            } else if (s_new > s_old * (1.0f + 4.0e-6f) && __double_as_longlong(kt) == 0ll) {
-                                settled = true;
-                                have = false;
-                            } else if (s_new > s_old * (1.0f + 4.0e-6f) && kt > 0.0 &&
-                                       (float)score_current * ((s_new - s_old) / s_new - 2.0e-6f) >
-                                           746.75f * (float)kt) {
-                                // new / old = sin(old) / sin(new) exactly as real numbers, so the score falls by
-                                // at least old * rel with rel = (s_new - s_old) / s_new - 2e-6 (the f32 sines
-                                // are within 6e-7 of the exact ones).  When that is more than 746.75 kT the
-                                // exponent is below -745.14, where cp_exp returns 0: rejected.
-                                settled = true;
-                                have = false;
-                            } else {
-                                sa_new = dev_sincos(new_val).s;
-                            }
-                        }
-                        if (!settled) {
-                            const double len = slot == 0 ? new_val : d.v[0], ratio = slot == 1 ? new_val : d.v[1];
-                            const double cell_area = sa_new * len * (len * ratio);  // cell.rs:190-192
-                            new_score = area_n / cell_area;                         // packed.rs:84
-                            have = accept_move_fast(new_score, score_current, kt, threshold);
-                        }
-                        if (!have) ++loop_rejections;
-                    }
-                }
+                if (!have) ++loop_rejections;
             }
         }
         if (!__any_sync(0xffffffffu, have)) {
             if (__all_sync(0xffffffffu, done)) break;
             continue;  // every lane used up its draws without a proposal to score
         }
-        // phase A (lanes holding a proposal): geometry and candidate generation
+        // the proposed state (lanes holding a proposal)
         double old_s = 0., old_c = 0.;
         const CellCache old_cc = cc;
-        cands.remaining = 0;
         if (have) {
             d.set(slot, new_val);
             if (slot == 2 || slot == 5) {  // the cell angle and the site angle are the only DOFs inside sin/cos
@@ -799,29 +765,17 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
                 } else {
                     old_s = t.sa; old_c = t.ca;
                     t.sa = sc.s; t.ca = sc.c;
-                    if constexpr (KIND != CP_LJ)
-                        new_score = area_n / (t.sa * d.v[0] * (d.v[0] * d.v[1]));  // cell.rs:190-192, packed.rs:84
                 }
             }
             if (slot <= 2) cc = cell_cache_of(d);
-            if constexpr (KIND != CP_LJ) {
-                t_place<KIND, NI, NS>(P, v, d, t);
-                t_sweep<KIND, NI, NS>(P, v, d, t, cc, cands);
-            }
         }
-        if constexpr (KIND == CP_LJ) {  // whole warp: lanes without a proposal keep step
+        {  // PotentialState::score, whole warp: lanes without a proposal work on the others' entries
             const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
             const double s = t_lj_score<NI>(P, g, d, t, cc, have);
             if (have) new_score = s;
         }
-        // phase B (whole warp): shape-pair tests, pooled over the warp's replicas
-        bool overlap = false;
-        if constexpr (KIND != CP_LJ) overlap = t_overlap_warp<KIND, NI, NS>(P, v, cands);
-        // phase C: Metropolis decision
+        // the Metropolis decision
         if (first) {
-            if constexpr (KIND != CP_LJ)
-                new_score = overlap ? __longlong_as_double(0x7FF8000000000000ll)
-                                    : area_n / (t.sa * d.v[0] * (d.v[0] * d.v[1]));
             score_current = new_score;
             const bool valid = score_current == score_current;
             if (active && !valid) atomicExch(K.error_flag, 1);
@@ -829,16 +783,9 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
             if (!done) next_stage();
             first = false;
         } else if (have) {
-            bool accepted;
-            if constexpr (KIND == CP_LJ) {
-                threshold = rng_draw_threshold_bits<RNG>(rng);
-                accepted = accept_move_fast(new_score, score_current, kt, threshold);
-            } else {
-                accepted = !overlap;  // the rule itself was evaluated before the overlap test
-            }
-            if (accepted) {
+            const unsigned long long threshold = rng_draw_threshold_bits<RNG>(rng);  // raw bits of draw #3
+            if (accept_move_fast(new_score, score_current, kt, threshold)) {
                 score_current = new_score;
-                if constexpr (KIND != CP_LJ) mine[(e_dof + slot) * 32] = new_val;
             } else {
                 d.set(slot, val);
                 if (slot == 5) { t.st = old_s; t.ct = old_c; }
@@ -876,7 +823,7 @@ struct THot {
 template <int RNG>
 __device__ __noinline__ void t_loop_end(const KParams &K, double *mine, int e_dof, unsigned long long replica,
                                         int n_basis, THot &h) {
-    double *sch = mine + (e_dof + 16) * 32;
+    double *sch = mine + (e_dof + kStSched) * 32;
     int packed = (int)__double_as_longlong(sch[kSchedStage * 32]);
     int stage = (packed & 0xff) - 1, convergence_count = packed >> 8;  // low byte: stage + 1 (0: none opened yet)
     unsigned long long loops_left = (unsigned long long)__double_as_longlong(sch[kSchedLoopsLeft * 32]);
@@ -912,8 +859,8 @@ __device__ __noinline__ void t_loop_end(const KParams &K, double *mine, int e_do
         }
         const KStage &S = K.stages[stage];
         // generate_basis(): bounds captured per optimise_state call (cell.rs:139-152)
-        mine[(e_dof + 6 + 0) * 32] = mine[(e_dof + 0) * 32];
-        mine[(e_dof + 6 + 1) * 32] = mine[(e_dof + 1) * 32];
+        mine[(e_dof + kStUpper + 0) * 32] = mine[(e_dof + 0) * 32];
+        mine[(e_dof + kStUpper + 1) * 32] = mine[(e_dof + 1) * 32];
         rng_begin_stage<RNG>(h.rng, K.seed_base, replica, n_basis);
         h.kt = S.kt_start;
         sch[kSchedStepRatio * 32] = 1.0;
@@ -941,7 +888,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     const KProblem &P = K.prob;
     const TView v = thread_view<KIND, NI, NS>(smem, P);
     thread_stage_constants<KIND, NI, NS>(v, P);
-    const int e_dof = TLayout<KIND, NI, NS>(P.n_items, P.n_syms).dof0();
+    const int e_dof = TLayout<KIND, NI, NS>(P).dof0();
     double *const mine = v.f64 + threadIdx.x;  // this lane's column of the f64 plane
     const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
     const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
@@ -954,19 +901,15 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
 #pragma unroll
     for (int i = 0; i < CP_MAX_DOF; ++i)
         mine[(e_dof + i) * 32] = (K.init_dof && active) ? K.init_dof[rep * CP_MAX_DOF + i] : P.dof[i];
-    mine[(e_dof + 6 + 2) * 32] = CP_PI / 2.;  // the upper bounds that do not depend on the stage
-    mine[(e_dof + 6 + 3) * 32] = 0.5;
-    mine[(e_dof + 6 + 4) * 32] = 0.5;
-    mine[(e_dof + 6 + 5) * 32] = CP_TAU;
     {
         const SinCos th = dev_sincos(mine[(e_dof + 5) * 32]), an = dev_sincos(mine[(e_dof + 2) * 32]);
-        mine[(e_dof + 12) * 32] = th.s;
-        mine[(e_dof + 13) * 32] = th.c;
-        mine[(e_dof + 14) * 32] = an.s;
-        mine[(e_dof + 15) * 32] = an.c;
+        mine[(e_dof + kStTrig + 0) * 32] = th.s;
+        mine[(e_dof + kStTrig + 1) * 32] = th.c;
+        mine[(e_dof + kStTrig + 2) * 32] = an.s;
+        mine[(e_dof + kStTrig + 3) * 32] = an.c;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) mine[(e_dof + 16 + i) * 32] = 0.;  // counters 0, no stage opened yet
+    for (int i = 0; i < 6; ++i) mine[(e_dof + kStSched + i) * 32] = 0.;  // counters 0, no stage opened yet
 
     THot h;
     h.score_current = 0.;
@@ -1012,7 +955,8 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
                 rng_draw_move<RNG>(h.rng, basis_index, sample);
                 slot = basis_to_slot(basis_index, n_cell);
                 const double val = mine[(e_dof + slot) * 32];
-                const double hi = mine[(e_dof + 6 + slot) * 32], lo = v.c_lo[slot];
+                const double *const hp = slot < 2 ? mine + (e_dof + kStUpper + slot) * 32 : v.c_lo + 6 + slot;
+                const double hi = *hp, lo = v.c_lo[slot];
                 new_val = val + h.step_scale * sample;
                 have = lo <= new_val && new_val <= hi;
                 if (!have) {
@@ -1022,7 +966,7 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
                 threshold = rng_draw_threshold_bits<RNG>(h.rng);
                 new_score = h.score_current;  // site moves leave the packing fraction as it is
                 if (slot <= 2) {
-                    double sa_new = mine[(e_dof + 14) * 32];
+                    double sa_new = mine[(e_dof + kStTrig + 2) * 32];
                     bool settled = false;
                     if (slot == 2) {
                         // Cell-angle move.  A single-precision sine (absolute error < 2^-21 on this
@@ -1074,10 +1018,10 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
             for (int i = 0; i < CP_MAX_DOF; ++i) d.v[i] = mine[(e_dof + i) * 32];
             d.set(slot, new_val);
             Trig t;
-            t.st = mine[(e_dof + 12) * 32];
-            t.ct = mine[(e_dof + 13) * 32];
-            t.sa = mine[(e_dof + 14) * 32];
-            t.ca = mine[(e_dof + 15) * 32];
+            t.st = mine[(e_dof + kStTrig + 0) * 32];
+            t.ct = mine[(e_dof + kStTrig + 1) * 32];
+            t.sa = mine[(e_dof + kStTrig + 2) * 32];
+            t.ca = mine[(e_dof + kStTrig + 3) * 32];
             if (slot == 2 || slot == 5) {  // the cell angle and the site angle are the only DOFs inside sin/cos
                 const SinCos sc = dev_sincos(new_val);
                 new_s = sc.s;
@@ -1115,12 +1059,12 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
                 h.score_current = new_score;
                 mine[(e_dof + slot) * 32] = new_val;
                 if (slot == 5) {
-                    mine[(e_dof + 12) * 32] = new_s;
-                    mine[(e_dof + 13) * 32] = new_c;
+                    mine[(e_dof + kStTrig + 0) * 32] = new_s;
+                    mine[(e_dof + kStTrig + 1) * 32] = new_c;
                 }
                 if (slot == 2) {
-                    mine[(e_dof + 14) * 32] = new_s;
-                    mine[(e_dof + 15) * 32] = new_c;
+                    mine[(e_dof + kStTrig + 2) * 32] = new_s;
+                    mine[(e_dof + kStTrig + 3) * 32] = new_c;
                 }
             } else {
                 ++h.loop_rejections;
@@ -1132,8 +1076,8 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
 #pragma unroll
         for (int i = 0; i < CP_MAX_DOF; ++i) r.dof[i] = mine[(e_dof + i) * 32];
         r.score = h.score_current;
-        r.rejections = (unsigned long long)__double_as_longlong(mine[(e_dof + 16 + kSchedRejections) * 32]);
-        r.moves = (unsigned long long)__double_as_longlong(mine[(e_dof + 16 + kSchedMoves) * 32]);
+        r.rejections = (unsigned long long)__double_as_longlong(mine[(e_dof + kStSched + kSchedRejections) * 32]);
+        r.moves = (unsigned long long)__double_as_longlong(mine[(e_dof + kStSched + kSchedMoves) * 32]);
         K.out[rep] = r;
     }
 }

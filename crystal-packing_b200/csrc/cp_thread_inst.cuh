@@ -5,7 +5,7 @@
 
 template <int KIND, int NI, int NS, int RNG>
 static cudaError_t thread_mc_launch(const KParams &K, cudaStream_t st) {
-    const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(K.prob.n_items, K.prob.n_syms);
+    const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(K.prob);
     const unsigned grid = (unsigned)((K.n_replicas + kThreadBlock - 1) / kThreadBlock);
     if constexpr (KIND == CP_LJ) {
         cudaError_t e = cp_allow_shared(mc_thread_lj_kernel<KIND, NI, NS, RNG>, bytes);
@@ -46,7 +46,7 @@ static cudaError_t thread_mc(const KParams &K, cudaStream_t st) {
 template <int KIND, int NI, int NS>
 static cudaError_t thread_score_launch(const KProblem &P, const double *dof, unsigned long long n, double *out,
                                        cudaStream_t st) {
-    const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(P.n_items, P.n_syms);
+    const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(P);
     cudaError_t e = cp_allow_shared(score_thread_kernel<KIND, NI, NS>, bytes);
     if (e != cudaSuccess) return e;
     score_thread_kernel<KIND, NI, NS><<<(unsigned)((n + kThreadBlock - 1) / kThreadBlock), kThreadBlock, bytes, st>>>(
@@ -63,7 +63,7 @@ template <int KIND, int NI, int NS>
 static cudaError_t thread_replay_launch(const KProblem &P, const double *init, const cp_move *mv,
                                         unsigned long long n_moves, unsigned long long n, cp_decision *out,
                                         cudaStream_t st) {
-    const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(P.n_items, P.n_syms);
+    const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(P);
     cudaError_t e = cp_allow_shared(replay_thread_kernel<KIND, NI, NS>, bytes);
     if (e != cudaSuccess) return e;
     replay_thread_kernel<KIND, NI, NS><<<(unsigned)((n + kThreadBlock - 1) / kThreadBlock), kThreadBlock, bytes, st>>>(

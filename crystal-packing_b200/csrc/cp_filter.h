@@ -228,6 +228,7 @@ struct CpfSweep {
     float af, bxf, byf;
     float wide2, narrow2;
     int shells;
+    float wide, inv_a, inv_by;  // cpf_sweep_pair_reach: sqrt(wide2) rounded up, 1 / af, 1 / byf
 };
 CPF_HD CpfSweep cpf_sweep_setup(float af, float bxf, float byf, float R, int shells) {
     CpfSweep s;
@@ -239,6 +240,9 @@ CPF_HD CpfSweep cpf_sweep_setup(float af, float bxf, float byf, float R, int she
     s.wide2 = r2x * r2x * (1.0f + delta);
     s.narrow2 = r2x * r2x * (1.0f - delta);
     s.shells = shells;
+    s.wide = sqrtf(s.wide2) * (1.0f + 1.0e-6f);
+    s.inv_a = 1.0f / af;
+    s.inv_by = 1.0f / byf;
     return s;
 }
 template <bool SELF>
@@ -266,6 +270,49 @@ CPF_HD unsigned long long cpf_sweep_pair(const CpfSweep &s, float d0x, float d0y
         if (sh + 7 > 32) hi |= sh >= 32 ? row << (sh - 32) : row >> (32 - sh);
     }
     return ((unsigned long long)hi << 32) | lo;
+}
+
+// The same mask from loops over the rows and columns in reach only, for multiplicity-4 groups (six
+// pair words and the self word per proposal, a handful of images in reach out of 48 each).  An image
+// with d2 <= wide2 has |vy| <= wide and |vx| <= wide, so its row lies in [(-wide - d0y) / byf,
+// (wide - d0y) / byf] and its column in [(-wide - x0) / af, (wide - x0) / af]; the bounds are
+// evaluated in single precision (relative error below 3e-7 of |d0y| / byf + wide / byf resp.
+// (|x0| + wide) / af) and widened by 0.01 + 1e-6 of those magnitudes before they are rounded
+// inwards and clamped to the shells, so every offset the straight-line sweep keeps is visited, with
+// the straight-line sweep's own expressions: the two return the same mask
+// (tests/filter_check.cpp compares them at every scored proposal).  Also reports the nearest image:
+// best / best_q are updated when a kept image is strictly nearer (first in bit order among equals).
+template <bool SELF>
+CPF_HD unsigned long long cpf_sweep_pair_reach(const CpfSweep &s, float d0x, float d0y, float &best, int &best_q) {
+    const float sh = (float)s.shells;
+    const float ymag = fmaf(fabsf(d0y) + s.wide, s.inv_by * 1.0e-6f, 0.01f);
+    const float ylo = fmaxf(fmaf(-s.wide - d0y, s.inv_by, -ymag), SELF ? -0.5f : -sh);
+    const float yhi = fminf(fmaf(s.wide - d0y, s.inv_by, ymag), sh);
+    const int iy0 = (int)ceilf(ylo), iy1 = (int)floorf(yhi);
+    unsigned long long m = 0ull;
+    for (int iy = iy0; iy <= iy1; ++iy) {
+        const float fiy = (float)iy;
+        const float vy = fmaf(fiy, s.byf, d0y), x0 = fmaf(fiy, s.bxf, d0x);
+        const float vy2 = vy * vy;
+        const float xmag = fmaf(fabsf(x0) + s.wide, s.inv_a * 1.0e-6f, 0.01f);
+        const float xlo = fmaxf(fmaf(-s.wide - x0, s.inv_a, -xmag), (SELF && iy == 0) ? 0.5f : -sh);
+        const float xhi = fminf(fmaf(s.wide - x0, s.inv_a, xmag), sh);
+        const int ix1 = (int)floorf(xhi);
+        for (int ix = (int)ceilf(xlo); ix <= ix1; ++ix) {
+            if (ix == 0 && iy == 0) continue;  // the zero offset is not an image (cell.rs:216-225)
+            const float vx = fmaf((float)ix, s.af, x0);
+            const float d2 = fmaf(vx, vx, vy2);
+            if (d2 <= s.wide2) {
+                const int q = (iy + 3) * 7 + (ix + 3);
+                m |= 1ull << q;
+                if (d2 < best) {
+                    best = d2;
+                    best_q = q;
+                }
+            }
+        }
+    }
+    return m;
 }
 
 #endif  // CP_FILTER_H

@@ -271,42 +271,53 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
     // Worth its instructions where a replica has many candidates (multiplicity 4: ten on average);
     // with two shapes per cell the plain order is as fast.
     constexpr bool kNearestFirst = NS == 0 || NS > 2;
-    float best = 3.0e38f;
-    int first = -1;
-    auto nearest = [&](unsigned long long bits, float d0x, float d0y, int w) {
+    if constexpr (kNearestFirst) {
+        // six pair words and the self word, a handful of images in reach out of 48 each: loops over
+        // the rows and columns in reach (cpf_sweep_pair_reach returns the straight-line sweep's mask)
+        float best = 3.0e38f;
+        int first = -1;
 #pragma unroll 1
-        while (bits) {
-            const int q = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            int ix, iy;
-            image_of_bit(q, ix, iy);
-            const float vy = fmaf((float)iy, s.byf, d0y), vx = fmaf((float)ix, s.af, fmaf((float)iy, s.bxf, d0x));
-            const float d2 = fmaf(vx, vx, vy * vy);
-            if (d2 < best) {
-                best = d2;
-                first = (w << 6) | q;
+        for (int w = 0; w < PW; ++w) {
+            const int ij = pair_of_word(w, L.N), i = ij >> 2, j = ij & 3;
+            const float d0x = (float)(g[(6 + 4 * j + 2) * 32] - g[(6 + 4 * i + 2) * 32]);
+            const float d0y = (float)(g[(6 + 4 * j + 3) * 32] - g[(6 + 4 * i + 3) * 32]);
+            int q = -1;
+            const unsigned long long bits = cpf_sweep_pair_reach<false>(s, d0x, d0y, best, q) | (1ull << kCentreBit);
+            // the in-cell pair competes with its own distance (the zero offset)
+            const float dc = fmaf(d0x, d0x, d0y * d0y);
+            if (dc < best) {
+                best = dc;
+                q = kCentreBit;
             }
+            if (q >= 0) first = (w << 6) | q;
+            c.st(w, bits);
+            count += __popcll(bits);
         }
-    };
-    // a rolled loop over the pair words: a single copy of the 48-offset sweep in the kernel
+        int q = -1;
+        const unsigned long long self = cpf_sweep_pair_reach<true>(s, 0.0f, 0.0f, best, q);
+        if (q >= 0) first = (PW << 6) | q;
+        c.st(PW, self);
+        count += __popcll(self) * L.N;
+        c.first = first;
+    } else {
+        // a rolled loop over the pair words: a single copy of the 48-offset sweep in the kernel
 #pragma unroll 1
-    for (int w = 0; w < PW; ++w) {
-        const int ij = pair_of_word(w, L.N), i = ij >> 2, j = ij & 3;
-        const float d0x = (float)(g[(6 + 4 * j + 2) * 32] - g[(6 + 4 * i + 2) * 32]);
-        const float d0y = (float)(g[(6 + 4 * j + 3) * 32] - g[(6 + 4 * i + 3) * 32]);
-        const unsigned long long bits = cpf_sweep_pair<false>(s, d0x, d0y) | (1ull << kCentreBit);
-        c.st(w, bits);
-        count += __popcll(bits);
-        if constexpr (kNearestFirst) nearest(bits, d0x, d0y, w);
+        for (int w = 0; w < PW; ++w) {
+            const int ij = pair_of_word(w, L.N), i = ij >> 2, j = ij & 3;
+            const float d0x = (float)(g[(6 + 4 * j + 2) * 32] - g[(6 + 4 * i + 2) * 32]);
+            const float d0y = (float)(g[(6 + 4 * j + 3) * 32] - g[(6 + 4 * i + 3) * 32]);
+            const unsigned long long bits = cpf_sweep_pair<false>(s, d0x, d0y) | (1ull << kCentreBit);
+            c.st(w, bits);
+            count += __popcll(bits);
+        }
+        const unsigned long long self = cpf_sweep_pair<true>(s, 0.0f, 0.0f);
+        c.st(PW, self);
+        count += __popcll(self) * L.N;
+        c.first = -1;
     }
-    const unsigned long long self = cpf_sweep_pair<true>(s, 0.0f, 0.0f);
-    c.st(PW, self);
-    count += __popcll(self) * L.N;
-    if constexpr (kNearestFirst) nearest(self, 0.0f, 0.0f, PW);
     c.cur = 0;
     c.phase = -1;
     c.remaining = count;
-    c.first = first;
 }
 
 // draws the next candidate of this lane (remaining > 0 guarantees there is one): the nearest one

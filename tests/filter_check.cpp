@@ -151,12 +151,29 @@ static int filtered_check(const orc_state *s, bool chain, Stats &st) {
     std::vector<unsigned long long> words;
     for (int i = 0; i < N; ++i)
         for (int j = i + 1; j < N; ++j) {
-            const unsigned long long bits =
-                cpf_sweep_pair<false>(sw, (float)(cx[j] - cx[i]), (float)(cy[j] - cy[i])) | (1ull << 24);
+            const float d0x = (float)(cx[j] - cx[i]), d0y = (float)(cy[j] - cy[i]);
+            const unsigned long long bits = cpf_sweep_pair<false>(sw, d0x, d0y) | (1ull << 24);
             words.push_back(bits);
             push_word(bits, i, j);
+            // the reach-limited loops (multiplicity-4 builds) must return the same mask
+            float best = 3.0e38f;
+            int bq = -1;
+            if ((cpf_sweep_pair_reach<false>(sw, d0x, d0y, best, bq) | (1ull << 24)) != bits) {
+                st.errors++;
+                std::fprintf(stderr, "reach sweep differs: pair (%d, %d), d0 = (%a, %a), a %a bx %a by %a shells %d\n", i, j,
+                             d0x, d0y, sw.af, sw.bxf, sw.byf, sw.shells);
+            }
         }
     const unsigned long long self = cpf_sweep_pair<true>(sw, 0.0f, 0.0f);
+    {
+        float best = 3.0e38f;
+        int bq = -1;
+        if (cpf_sweep_pair_reach<true>(sw, 0.0f, 0.0f, best, bq) != self) {
+            st.errors++;
+            std::fprintf(stderr, "reach sweep differs: self word, a %a bx %a by %a shells %d\n", sw.af, sw.bxf, sw.byf,
+                         sw.shells);
+        }
+    }
     for (int i = 0; i < N; ++i) push_word(self, i, i);
     // the sweep must not miss anything the reference tests: every ordered pair, every image within
     // `shells` that passes the f64 filter (packed.rs:152-157) is in the list, itself or as its mirror
@@ -279,7 +296,44 @@ static int filtered_check(const orc_state *s, bool chain, Stats &st) {
     return overlap ? 1 : 0;
 }
 
+// `filter_check sweep <cases>`: the reach-limited image sweep against the straight-line one on random
+// cells, extreme ones included (lengths down to the lower bound 0.01, ratios from 0.1 to 100, every
+// cell angle, displacements anywhere in the cell, enclosing radii from 0.05 to 5).
+static int sweep_stress(unsigned long long cases) {
+    unsigned long long x = 0x9E3779B97F4A7C15ull, errors = 0, kept = 0;
+    auto rnd = [&]() {  // xorshift64*, uniform in [0, 1)
+        x ^= x >> 12;
+        x ^= x << 25;
+        x ^= x >> 27;
+        return (double)((x * 0x2545F4914F6CDD1Dull) >> 11) * (1.0 / 9007199254740992.0);
+    };
+    for (unsigned long long c = 0; c < cases; ++c) {
+        const double a = rnd() < 0.2 ? 0.01 + rnd() * 0.1 : std::exp(std::log(0.01) + rnd() * std::log(2000.0));
+        const double ratio = rnd() < 0.8 ? 0.1 + 0.9 * rnd() : std::exp(std::log(0.1) + rnd() * std::log(1000.0));
+        const double angle = M_PI / 4 + rnd() * M_PI / 4, b = a * ratio;
+        const double R = rnd() < 0.5 ? 1.0 : 0.05 + rnd() * 4.95;
+        const int shells = 1 + (int)(rnd() * 3.0);
+        const CpfSweep sw = cpf_sweep_setup((float)a, (float)(b * std::cos(angle)), (float)(b * std::sin(angle)), (float)R, shells);
+        const double fx = rnd() * 2.0 - 1.0, fy = rnd() * 2.0 - 1.0;  // difference of two wrapped positions
+        const float d0x = (float)(fx * a + fy * b * std::cos(angle)), d0y = (float)(fy * b * std::sin(angle));
+        float best = 3.0e38f;
+        int q = -1;
+        const unsigned long long m0 = cpf_sweep_pair<false>(sw, d0x, d0y), m1 = cpf_sweep_pair_reach<false>(sw, d0x, d0y, best, q);
+        best = 3.0e38f;
+        const unsigned long long s0 = cpf_sweep_pair<true>(sw, 0.0f, 0.0f), s1 = cpf_sweep_pair_reach<true>(sw, 0.0f, 0.0f, best, q);
+        kept += __builtin_popcountll(m0);
+        if (m0 != m1 || s0 != s1) {
+            if (errors++ < 5)
+                std::fprintf(stderr, "case %llu: a %g ratio %g angle %g R %g shells %d d0 (%g, %g): %llx vs %llx, self %llx vs %llx\n",
+                             c, a, ratio, angle, R, shells, d0x, d0y, m0, m1, s0, s1);
+        }
+    }
+    std::printf("{\"cases\": %llu, \"errors\": %llu, \"kept\": %llu}\n", cases, errors, kept);
+    return errors ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc == 3 && !std::strcmp(argv[1], "sweep")) return sweep_stress(std::strtoull(argv[2], nullptr, 10));
     if (argc < 6) {
         std::fprintf(stderr, "usage: %s polygon|trimer|circle|star sides group replicas steps [kt_start kt_finish]\n", argv[0]);
         return 2;

@@ -63,3 +63,12 @@ def test_certificates_are_sound(checker, shape, sides, group, replicas, steps, e
     assert stats["scored"] > 1000 and stats["clear"] + stats["hit"] > 0
     # the certificates decide most shape pairs; the f64 path is the exception
     assert stats["ambiguous"] < 0.5 * (stats["clear"] + stats["hit"] + stats["ambiguous"])
+
+
+def test_reach_limited_sweep_equals_straight_line_sweep(checker):
+    """cpf_sweep_pair_reach (multiplicity-4 builds) returns the mask of cpf_sweep_pair on two million
+    random cells, degenerate ones included."""
+    out = subprocess.run([checker, "sweep", "2000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    stats = json.loads(out.stdout.splitlines()[0])
+    assert stats["errors"] == 0 and stats["kept"] > stats["cases"]

@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--config-steps", type=int, default=2, help="timed passes of each extra configuration")
     ap.add_argument("--c5-total", type=int, default=8388608, help="replicas of the C5 sweep (rounded down to 70 equal cells)")
     ap.add_argument("--c5-mc-steps", type=int, default=1000)
+    ap.add_argument("--c5-streams", type=int, default=2, choices=[1, 2],
+                    help="contexts per GPU the C5 chunks alternate over (2: cell tails overlap)")
     return ap.parse_args()
 
 
@@ -260,6 +262,25 @@ class Bench:
             self._best_dev = self.torch.as_tensor(BestView(ptr), device=self.dev)
         return self._best_dev
 
+    def second_lane(self):
+        """(engine, stream, device cp_best view) of a second context on this GPU"""
+        if not hasattr(self, "_lane2"):
+            torch, cp, cpd = self.torch, self.cp, self.cpd
+            eng = cp.Engine(self.local_rank, lanes=self.args.lanes)
+            stream = torch.cuda.Stream(device=self.local_rank)
+            eng.set_stream(stream.cuda_stream)
+            state = cp.PackedState.from_group(cp.LineShape.polygon(4), "p1")
+            eng.prepare(state._problem, cp.BuildOptimiser.cli_defaults().pipeline(), 32)
+            _, ptr = eng.device_buffers()
+
+            class BestView:
+                def __init__(self, ptr):
+                    self.__cuda_array_interface__ = {"shape": (cpd.BEST_BYTES,), "typestr": "|u1",
+                                                     "data": (ptr, False), "version": 2}
+
+            self._lane2 = (eng, stream, torch.as_tensor(BestView(ptr), device=self.dev))
+        return self._lane2
+
     def barrier(self):
         if self.dist:
             self.dist.barrier()
@@ -384,20 +405,35 @@ def run_c5(B):
     template = nan_rec.to(B.dev).repeat(slots)
     torch.cuda.synchronize()
 
+    # Two contexts, two streams on this GPU: the chunks alternate between them, so the tail of one
+    # cell's kernel (its last, partly filled wave of blocks) overlaps the start of the next cell's.
+    lanes = [(B.eng, B.stream, best_dev)] + ([B.second_lane()] if args.c5_streams > 1 else [])
+
     def run_chunks(mine, timed_each):
-        """launches this rank's chunks back to back; keeps each chunk's cp_best in its slot"""
+        """launches this rank's chunks, alternating over the lanes (one lane, back to back, when each
+        chunk is timed on its own); keeps each chunk's cp_best in its slot"""
         with torch.cuda.stream(B.stream):
             bests = template.clone()
+            ready = torch.cuda.Event()
+            ready.record(B.stream)
         times = {}
+        use = lanes[:1] if timed_each else lanes
+        for _, st, _ in use[1:]:
+            st.wait_event(ready)
         for k, ci in enumerate(mine):
             c, begin, count = chunks[ci]
-            B.eng.prepare(states[c]._problem, schedules, count, replica_begin=begin, rng=cp.RNG_PHILOX)
-            B.eng.launch()
-            with torch.cuda.stream(B.stream):
-                bests[k * cpd.BEST_BYTES:(k + 1) * cpd.BEST_BYTES].copy_(best_dev)
+            eng, st, bdev = use[k % len(use)]
+            eng.prepare(states[c]._problem, schedules, count, replica_begin=begin, rng=cp.RNG_PHILOX)
+            eng.launch()
+            with torch.cuda.stream(st):
+                bests[k * cpd.BEST_BYTES:(k + 1) * cpd.BEST_BYTES].copy_(bdev)
             if timed_each:
-                B.stream.synchronize()
-                times[ci] = B.eng.timing_kernel_ms()
+                st.synchronize()
+                times[ci] = eng.timing_kernel_ms()
+        for _, st, _ in use[1:]:  # the launch stream closes the pass: it waits for the other lane
+            done = torch.cuda.Event()
+            done.record(st)
+            B.stream.wait_event(done)
         return bests, times
 
     # calibration = warm-up pass 1 (also loads every kernel build this rank will launch)
@@ -454,6 +490,7 @@ def run_c5(B):
         "rank_spread": (max(per_rank) - min(per_rank)) / max(per_rank),
         "chunks": len(chunks), "chunks_per_rank": [len(a) for a in assign],
         "balance": "longest-first by measured chunk time (calibration = first warm-up pass)",
+        "streams_per_gpu": len(lanes),
         "planned_loads_ms": est_loads, "steps": args.config_steps, "warmup": warm + 1,
         "gpu_launches": 3 * len(mine) * args.config_steps,
         "limit": "heaviest cells: " + ", ".join(

@@ -640,7 +640,7 @@ __host__ __device__ inline size_t thread_block_shared_bytes(const KProblem &P) {
 // Register budget = minimum resident blocks per SM (hard shapes: 14 warps per SM hold all 2,048
 // warps of a 65,536-replica batch at once).
 constexpr int thread_min_blocks(int kind, int ni) {
-    return kind == CP_LJ ? 10 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 9 ? 10 : 8)));
+    return kind == CP_LJ ? 10 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 11 ? 10 : 8)));
 }
 // proposals a lane may draw per pass before the warp goes on to score what it has: the draw loop
 // is divergent (lanes leave it as they find a proposal worth scoring), so its tail is cut

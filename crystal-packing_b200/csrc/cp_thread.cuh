@@ -652,8 +652,8 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
     static_assert(KIND == CP_LJ, "LJ only: hard shapes run mc_thread_kernel");
     extern __shared__ double smem[];
     const KProblem &P = K.prob;
-    const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
-    const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
+    const unsigned long long rep = (unsigned long long)blockIdx.x * K.warp_fill + threadIdx.x;
+    const bool active = (int)threadIdx.x < K.warp_fill && rep < K.n_replicas;  // idle lanes stay in the warp-wide votes, doing nothing
     const unsigned long long replica = K.replica_begin + (active ? rep : 0ull);
 
     Dof d;
@@ -901,8 +901,8 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     thread_stage_constants<KIND, NI, NS>(v, P);
     const int e_dof = TLayout<KIND, NI, NS>(P).dof0();
     double *const mine = v.f64 + threadIdx.x;  // this lane's column of the f64 plane
-    const unsigned long long rep = (unsigned long long)blockIdx.x * kThreadBlock + threadIdx.x;
-    const bool active = rep < K.n_replicas;  // tail lanes stay in the warp-wide votes, doing nothing
+    const unsigned long long rep = (unsigned long long)blockIdx.x * K.warp_fill + threadIdx.x;
+    const bool active = (int)threadIdx.x < K.warp_fill && rep < K.n_replicas;  // idle lanes stay in the warp-wide votes, doing nothing
     const unsigned long long replica = K.replica_begin + (active ? rep : 0ull);
     const int n_cell = n_cell_dof(P.family);
     const int n_basis = n_cell + 3;

@@ -4,19 +4,41 @@
 #include "cp_thread.cuh"
 
 template <int KIND, int NI, int NS, int RNG>
-static cudaError_t thread_mc_launch(const KParams &K, cudaStream_t st) {
+static cudaError_t thread_mc_launch(const KParams &K0, cudaStream_t st) {
+    KParams K = K0;
     const size_t bytes = thread_block_shared_bytes<KIND, NI, NS>(K.prob);
-    const unsigned grid = (unsigned)((K.n_replicas + kThreadBlock - 1) / kThreadBlock);
-    if constexpr (KIND == CP_LJ) {
-        cudaError_t e = cp_allow_shared(mc_thread_lj_kernel<KIND, NI, NS, RNG>, bytes);
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cp_allow_shared(kernel, bytes);
         if (e != cudaSuccess) return e;
-        mc_thread_lj_kernel<KIND, NI, NS, RNG><<<grid, kThreadBlock, bytes, st>>>(K);
-    } else {
-        cudaError_t e = cp_allow_shared(mc_thread_kernel<KIND, NI, NS, RNG>, bytes);
-        if (e != cudaSuccess) return e;
-        mc_thread_kernel<KIND, NI, NS, RNG><<<grid, kThreadBlock, bytes, st>>>(K);
-    }
-    return cudaGetLastError();
+        if (K.warp_fill < 1 || K.warp_fill > kThreadBlock) {
+            // Replicas per warp.  A batch that fits the GPU's warp slots at once is spread over a whole
+            // number of warps per scheduler (4 per SM): every scheduler carries the same load - 65,536
+            // replicas are 3.46 warps of 32 per scheduler, or 4 warps of 28 on each - and a small batch
+            // runs in more, shorter warps (the pool rounds of a warp scale with its replicas).  Never
+            // below 8 replicas per warp, where the pooled tests run out of lanes; batches larger than
+            // the slots run full warps in several waves.
+            int per_sm = 0, dev = 0, sms = 0;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreadBlock, bytes)) != cudaSuccess) return e;
+            if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+            if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+            const unsigned long long slots = (unsigned long long)(per_sm > 0 ? per_sm : 1) * (unsigned long long)sms;
+            const unsigned long long full = (K.n_replicas + kThreadBlock - 1) / kThreadBlock, sched = 4ull * (unsigned long long)sms;
+            K.warp_fill = kThreadBlock;
+            if (full <= slots) {
+                unsigned long long warps = (full + sched - 1) / sched * sched;
+                if (warps > slots) warps = slots;
+                const unsigned long long fill = (K.n_replicas + warps - 1) / warps;
+                K.warp_fill = fill >= (unsigned long long)kThreadBlock ? kThreadBlock : (fill < 8 ? 8 : (int)fill);
+            }
+        }
+        const unsigned grid = (unsigned)((K.n_replicas + K.warp_fill - 1) / K.warp_fill);
+        kernel<<<grid, kThreadBlock, bytes, st>>>(K);
+        return cudaGetLastError();
+    };
+    if constexpr (KIND == CP_LJ)
+        return launch(mc_thread_lj_kernel<KIND, NI, NS, RNG>);
+    else
+        return launch(mc_thread_kernel<KIND, NI, NS, RNG>);
 }
 
 // Builds with a compile-time component count exist for multiplicities 1, 2 and 4 (every plane group

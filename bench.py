@@ -645,7 +645,7 @@ def run_b200(args, rank, local_rank, world):
                         "active_lanes_per_instruction": ex["thread_inst_per_inst"],
                         "from_profile": ex["from_profile"],
                         "executed_note": "per-move instruction counts of the ncu capture x this run's moves/s; the kernel "
-                                         "is bound by issue slots and fixed-latency dependencies at ~3 warps per "
+                                         "is bound by issue slots and fixed-latency dependencies at 4 warps per "
                                          "scheduler, not by an FP pipe",
                     })
                     traffic = ex["dram_bytes_per_launch"]

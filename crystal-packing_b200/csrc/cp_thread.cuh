@@ -612,7 +612,7 @@ template <int KIND, int NI, int NS>
 __device__ __forceinline__ double t_state_score(const KProblem &P, const TView &v, double *smem, const Dof &d,
                                                 const Trig &t, bool live) {
     if constexpr (KIND == CP_LJ) {
-        const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
+        const TGeo g = lj_geo(smem, P);
         return t_lj_score<NI>(P, g, d, t, cell_cache_of(d), live);
     } else {
         TCands<NS> c;
@@ -630,7 +630,7 @@ __device__ __forceinline__ double t_state_score(const KProblem &P, const TView &
 // shared memory of a block
 template <int KIND, int NI, int NS>
 __host__ __device__ inline size_t thread_block_shared_bytes(const KProblem &P) {
-    if (KIND == CP_LJ) return lj_block_bytes(P.n_items, P.n_syms);
+    if (KIND == CP_LJ) return lj_block_bytes(P);
     return TLayout<KIND, NI, NS>(P).bytes();
 }
 
@@ -640,7 +640,7 @@ __host__ __device__ inline size_t thread_block_shared_bytes(const KProblem &P) {
 // Register budget = minimum resident blocks per SM (hard shapes: 14 warps per SM hold all 2,048
 // warps of a 65,536-replica batch at once).
 constexpr int thread_min_blocks(int kind, int ni) {
-    return kind == CP_LJ ? 10 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 11 ? 10 : 8)));
+    return kind == CP_LJ ? 14 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 11 ? 10 : 8)));
 }
 // proposals a lane may draw per pass before the warp goes on to score what it has: the draw loop
 // is divergent (lanes leave it as they find a proposal worth scoring), so its tail is cut
@@ -781,7 +781,7 @@ mc_thread_lj_kernel(const __grid_constant__ KParams K) {
             if (slot <= 2) cc = cell_cache_of(d);
         }
         {  // PotentialState::score, whole warp: lanes without a proposal work on the others' entries
-            const TGeo g{smem + threadIdx.x, 4 + P.n_syms * 4};
+            const TGeo g = lj_geo(smem, P);
             const double s = t_lj_score<NI>(P, g, d, t, cc, have);
             if (have) new_score = s;
         }

@@ -9,52 +9,82 @@
 // and sites without cutoff take the plain loops
 constexpr int kLjQueueSites = 4;
 
-// doubles of shared memory each LJ thread needs: four cell values, per image fx fy cx cy, per site
-// the rotated position (f64), then the same positions in single precision (one double = x, y of a
-// site), the image masks of the shape pairs i < j and of a shape with itself (64 bits each) and two
+// doubles of shared memory each LJ thread needs: four cell values, per image fx fy cx cy, per stored
+// site the rotated position (f64), then the same positions in single precision (one double = x, y of
+// a site), the image masks of the shape pairs i < j and of a shape with itself (64 bits each) and two
 // elements of single-precision sweep parameters (af, bxf | byf, ec).  The warp's pool (32 entries,
 // 32 energies) follows the 32 columns.
+// Stored sites: those of image 0 only when every operator's rotation part is operator 0's with the
+// signs of its rows flipped (KProblem::signed_images - all seven plane groups of the reference): the
+// rotated sites of image s are then image 0's with those signs, bit for bit up to the sign of a zero,
+// which no energy can see (a rotated coordinate only enters a sum with the image's position and the
+// difference of two such sums is squared).  Otherwise the sites of every image.
 __host__ __device__ inline int lj_mask_words(int n_syms) { return n_syms * (n_syms - 1) / 2 + 1; }
-__host__ __device__ inline int lj_geo_doubles(int n_items, int n_syms) {
-    return 4 + n_syms * 4 + n_syms * n_items * 2 + n_syms * n_items + lj_mask_words(n_syms) + 2;
+__host__ __device__ inline int lj_stored_images(const KProblem &P) { return P.signed_images ? 1 : P.n_syms; }
+__host__ __device__ inline int lj_geo_doubles(const KProblem &P) {
+    return 4 + P.n_syms * 4 + lj_stored_images(P) * P.n_items * 3 + lj_mask_words(P.n_syms) + 2;
 }
-__host__ __device__ inline size_t lj_block_bytes(int n_items, int n_syms) {
-    return sizeof(double) * 32 * (size_t)(lj_geo_doubles(n_items, n_syms) + 1) + 32 * sizeof(unsigned);
+__host__ __device__ inline size_t lj_block_bytes(const KProblem &P) {
+    return sizeof(double) * 32 * (size_t)(lj_geo_doubles(P) + 1) + 32 * sizeof(unsigned);
 }
+
+// sign flips as integer operations (the FP64 pipe is what the dense LJ regime is short of)
+__device__ __forceinline__ double lj_flip(double v, unsigned sign) {
+    return __hiloint2double(__double2hiint(v) ^ (int)sign, __double2loint(v));
+}
+__device__ __forceinline__ float lj_flipf(float v, unsigned sign) { return __uint_as_float(__float_as_uint(v) ^ sign); }
 
 // a thread's column of the [element][thread] planes (STRIDE = 32)
 template <int STRIDE>
 struct TGeoT {
     double *base;  // element e is base[e * STRIDE]
-    int comp0;     // first component element (= 4 + N * 4); images start at element 4
+    int comp0;     // first site element (= 4 + N * 4); images start at element 4
+    int stored;    // rotated sites stored: (images stored) * n
+    int words;     // mask words
+    int geo;       // doubles per column
     __device__ __forceinline__ double ld(int e) const { return base[e * STRIDE]; }
     __device__ __forceinline__ void st(int e, double v) const { base[e * STRIDE] = v; }
-    // single-precision copy of the rotated site c (= image * n + site): element comp0 + 2 * total + c
-    __device__ __forceinline__ float2 ldf(int total, int c) const {
-        return *reinterpret_cast<const float2 *>(base + (comp0 + 2 * total + c) * STRIDE);
+    // single-precision copy of the stored site c: element comp0 + 2 * stored + c
+    __device__ __forceinline__ float2 ldf(int c) const {
+        return *reinterpret_cast<const float2 *>(base + (comp0 + 2 * stored + c) * STRIDE);
     }
-    __device__ __forceinline__ void stf(int total, int c, float x, float y) const {
-        *reinterpret_cast<float2 *>(base + (comp0 + 2 * total + c) * STRIDE) = make_float2(x, y);
+    __device__ __forceinline__ void stf(int c, float x, float y) const {
+        *reinterpret_cast<float2 *>(base + (comp0 + 2 * stored + c) * STRIDE) = make_float2(x, y);
     }
-    // image mask m: element comp0 + 3 * total + m
-    __device__ __forceinline__ unsigned long long *mask(int total, int m) const {
-        return reinterpret_cast<unsigned long long *>(base + (comp0 + 3 * total + m) * STRIDE);
+    // image mask m: element comp0 + 3 * stored + m
+    __device__ __forceinline__ unsigned long long *mask(int m) const {
+        return reinterpret_cast<unsigned long long *>(base + (comp0 + 3 * stored + m) * STRIDE);
     }
     // sweep parameters: two elements behind the masks
-    __device__ __forceinline__ float2 *fpar(int total, int n_syms, int e) const {
-        return reinterpret_cast<float2 *>(base + (comp0 + 3 * total + lj_mask_words(n_syms) + e) * STRIDE);
+    __device__ __forceinline__ float2 *fpar(int e) const {
+        return reinterpret_cast<float2 *>(base + (comp0 + 3 * stored + words + e) * STRIDE);
     }
     // the same column of another lane of the warp
-    __device__ __forceinline__ TGeoT of(unsigned lane) const { return TGeoT{base - threadIdx.x + lane, comp0}; }
+    __device__ __forceinline__ TGeoT of(unsigned lane) const {
+        TGeoT o = *this;
+        o.base = base - threadIdx.x + lane;
+        return o;
+    }
     // the warp's pool behind the 32 columns (call on the lane's OWN column): 32 energies, 32 entries
-    __device__ __forceinline__ double *pool_energies(int n_items, int n_syms) const {
-        return base - threadIdx.x + 32 * lj_geo_doubles(n_items, n_syms);
-    }
-    __device__ __forceinline__ unsigned *pool_entries(int n_items, int n_syms) const {
-        return reinterpret_cast<unsigned *>(pool_energies(n_items, n_syms) + 32);
-    }
+    __device__ __forceinline__ double *pool_energies() const { return base - threadIdx.x + 32 * geo; }
+    __device__ __forceinline__ unsigned *pool_entries() const { return reinterpret_cast<unsigned *>(pool_energies() + 32); }
 };
 using TGeo = TGeoT<32>;
+// this thread's column
+__device__ __forceinline__ TGeo lj_geo(double *smem, const KProblem &P) {
+    return TGeo{smem + threadIdx.x, 4 + P.n_syms * 4, lj_stored_images(P) * P.n_items, lj_mask_words(P.n_syms), lj_geo_doubles(P)};
+}
+// Where the rotated sites of image s are stored and the signs to apply to them: element of site 0 (x;
+// y follows), sign masks of x and y.
+struct LjImage {
+    int e0;
+    unsigned sx, sy;
+};
+__device__ __forceinline__ LjImage lj_image(const KProblem &P, const TGeo &g, int n, int s) {
+    if (g.stored == n && P.n_syms > 1)  // image 0's sites with this image's row signs
+        return LjImage{g.comp0, __float_as_uint(P.sgnf[s][0]) & 0x80000000u, __float_as_uint(P.sgnf[s][1]) & 0x80000000u};
+    return LjImage{g.comp0 + s * n * 2, 0u, 0u};
+}
 
 // per-replica values that depend on the cell DOFs only, kept across moves
 struct CellCache {
@@ -92,6 +122,7 @@ __device__ __forceinline__ void lj_build_geometry(const KProblem &P, TGeo g, con
         g.st(4 + s * 4 + 1, fy);
         g.st(4 + s * 4 + 2, fx * a + yb * t.ca);  // cell.rs:258-263
         g.st(4 + s * 4 + 3, yb * t.sa);
+        if (s * n >= g.stored) continue;  // signed images: the sites of image 0 serve every image
 #pragma unroll
         for (int k = 0; k < (NI > 0 ? NI : CP_MAX_ITEMS); ++k) {
             if (NI == 0 && k >= n) break;
@@ -100,7 +131,7 @@ __device__ __forceinline__ void lj_build_geometry(const KProblem &P, TGeo g, con
             const double rx = m00 * it[0] + m01 * it[1], ry = m10 * it[0] + m11 * it[1];
             g.st(e + 0, rx);  // Transform * Point without its translation
             g.st(e + 1, ry);
-            g.stf(N * n, s * n + k, (float)rx, (float)ry);  // the pre-filter's copy (t_lj_score)
+            g.stf(s * n + k, (float)rx, (float)ry);  // the pre-filter's copy (t_lj_score)
         }
     }
 }
@@ -110,7 +141,8 @@ __device__ __forceinline__ void lj_build_geometry(const KProblem &P, TGeo g, con
 template <int NI>
 __device__ __forceinline__ double t_shape_energy(const KProblem &P, TGeo g, int i, int j, double X, double Y) {
     const int n = NI > 0 ? NI : P.n_items;
-    const int ei = g.comp0 + i * n * 2, ej = g.comp0 + j * n * 2;
+    const LjImage Ii = lj_image(P, g, n, i), Ij = lj_image(P, g, n, j);
+    const int ei = Ii.e0, ej = Ij.e0;
     const double cx = g.ld(4 + i * 4 + 2), cy = g.ld(4 + i * 4 + 3);
     double e = 0.;
     // the run-time-count build (NI = 0) keeps these loops rolled: the function is inlined at nine
@@ -119,12 +151,12 @@ __device__ __forceinline__ double t_shape_energy(const KProblem &P, TGeo g, int 
 #pragma unroll(NI > 0 ? NI : 1)
     for (int k = 0; k < (NI > 0 ? NI : CP_MAX_ITEMS); ++k) {
         if (NI == 0 && k >= n) break;
-        const double sx = g.ld(ei + k * 2 + 0) + cx, sy = g.ld(ei + k * 2 + 1) + cy;
+        const double sx = lj_flip(g.ld(ei + k * 2 + 0), Ii.sx) + cx, sy = lj_flip(g.ld(ei + k * 2 + 1), Ii.sy) + cy;
         const double *it = P.items[k];
 #pragma unroll(NI > 0 ? NI : 1)
         for (int l = 0; l < (NI > 0 ? NI : CP_MAX_ITEMS); ++l) {
             if (NI == 0 && l >= n) break;
-            const double ox = g.ld(ej + l * 2 + 0) + X, oy = g.ld(ej + l * 2 + 1) + Y;
+            const double ox = lj_flip(g.ld(ej + l * 2 + 0), Ij.sx) + X, oy = lj_flip(g.ld(ej + l * 2 + 1), Ij.sy) + Y;
             e += lj_pair(sx - ox, sy - oy, it[2], it[3], it[4], P.lj_shift[k]);
         }
     }
@@ -270,8 +302,10 @@ __device__ __forceinline__ unsigned long long lj_sweep_pair(const LjSweep &s, fl
 template <int NI, class Geo>
 __device__ __forceinline__ unsigned lj_prefilter(const KProblem &P, Geo g, int N, int i, int j, int qb) {
     constexpr int NN = NI > 0 ? NI : kLjQueueSites;
-    const int n = NI > 0 ? NI : P.n_items, total = N * n;
-    const float2 p0 = *g.fpar(total, N, 0), p1 = *g.fpar(total, N, 1);  // (af, bxf), (byf, ec)
+    const int n = NI > 0 ? NI : P.n_items;
+    const LjImage Ii = lj_image(P, g, n, i), Ij = lj_image(P, g, n, j);
+    const int ci = (Ii.e0 - g.comp0) >> 1, cj = (Ij.e0 - g.comp0) >> 1;  // first stored site of either image
+    const float2 p0 = *g.fpar(0), p1 = *g.fpar(1);  // (af, bxf), (byf, ec)
     const float d0x = (float)(g.ld(4 + j * 4 + 2) - g.ld(4 + i * 4 + 2));
     const float d0y = (float)(g.ld(4 + j * 4 + 3) - g.ld(4 + i * 4 + 3));
     const int cix = (qb * 37) >> 8;
@@ -280,9 +314,9 @@ __device__ __forceinline__ unsigned lj_prefilter(const KProblem &P, Geo g, int N
     float bx[NN], by[NN];
 #pragma unroll
     for (int l = 0; l < NN; ++l) {
-        const float2 B = g.ldf(total, j * n + (l < n ? l : 0));
-        bx[l] = B.x + Dx;
-        by[l] = B.y + Dy;
+        const float2 B = g.ldf(cj + (l < n ? l : 0));
+        bx[l] = lj_flipf(B.x, Ij.sx) + Dx;
+        by[l] = lj_flipf(B.y, Ij.sy) + Dy;
     }
     unsigned m = 0u;
 #pragma unroll
@@ -291,7 +325,8 @@ __device__ __forceinline__ unsigned lj_prefilter(const KProblem &P, Geo g, int N
         const double cut = P.items[k < n ? k : 0][4];
         const float c = (float)cut * (1.0f + 1e-6f) + 2.0f * p1.y;
         const float lim = cut == cut ? c * c * (1.0f + 1e-6f) : 3.0e38f;
-        const float2 A = g.ldf(total, i * n + (k < n ? k : 0));
+        const float2 A0 = g.ldf(ci + (k < n ? k : 0));
+        const float2 A = make_float2(lj_flipf(A0.x, Ii.sx), lj_flipf(A0.y, Ii.sy));
 #pragma unroll
         for (int l = 0; l < NN; ++l) {
             const float dx = A.x - bx[l], dy = A.y - by[l];
@@ -309,10 +344,10 @@ __device__ __forceinline__ int lj_pair_of(int p, int N) {
 }
 // the image mask of the ordered pair (i, j): stored for i < j, mirrored for i > j, one for all i == j
 template <class Geo>
-__device__ __forceinline__ unsigned long long lj_image_mask(Geo g, int N, int total, int i, int j) {
+__device__ __forceinline__ unsigned long long lj_image_mask(Geo g, int N, int i, int j) {
     const int PW = N * (N - 1) / 2;
     const int lo = i < j ? i : j, hi = i < j ? j : i;
-    const unsigned long long m = *g.mask(total, i == j ? PW : lo * N - lo * (lo + 1) / 2 + (hi - lo - 1));
+    const unsigned long long m = *g.mask(i == j ? PW : lo * N - lo * (lo + 1) / 2 + (hi - lo - 1));
     return i > j ? __brevll(m) >> 15 : m;  // bit q <-> bit 48 - q
 }
 
@@ -341,10 +376,10 @@ __device__ __forceinline__ void lj_pool_quota(int want, int &take, int &slot, in
 template <int NI>
 __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, const Dof &d, const Trig &t, bool live) {
     const unsigned lane = threadIdx.x & 31u;
-    const int N = P.n_syms, n = NI > 0 ? NI : P.n_items, total = N * n;
+    const int N = P.n_syms, n = NI > 0 ? NI : P.n_items;
     const int PW = N * (N - 1) / 2;
-    unsigned *const pool = g.pool_entries(P.n_items, N);
-    double *const E = g.pool_energies(P.n_items, N);
+    unsigned *const pool = g.pool_entries();
+    double *const E = g.pool_energies();
     // 1. image masks.  The in-cell pairs i < j (potential.rs:88-96) pass the same reach test: beyond it
     // every site pair is outside its cutoff and the shape-pair energy is exactly +0.0.
     int cands = 0;          // candidates this lane still has to hand out
@@ -352,15 +387,15 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
     unsigned nonempty = 0u; // ordered pairs (i, j) with an image in reach, bit = i * N + j
     if (live) {
         const LjSweep S = lj_sweep_setup(P, d, t);
-        *g.fpar(total, N, 0) = make_float2(S.af, S.bxf);
-        *g.fpar(total, N, 1) = make_float2(S.byf, S.ec);
+        *g.fpar(0) = make_float2(S.af, S.bxf);
+        *g.fpar(1) = make_float2(S.byf, S.ec);
         int m = 0;
         for (int i = 0; i < N; ++i)
             for (int j = i + 1; j < N; ++j, ++m) {
                 const float d0x = (float)(g.ld(4 + j * 4 + 2) - g.ld(4 + i * 4 + 2));
                 const float d0y = (float)(g.ld(4 + j * 4 + 3) - g.ld(4 + i * 4 + 3));
                 const unsigned long long bits = lj_sweep_pair<false>(S, d0x, d0y);
-                *g.mask(total, m) = bits;
+                *g.mask(m) = bits;
                 cands += 2 * __popcll(bits);  // (i, j) and its mirror (j, i)
                 if (bits) nonempty |= (1u << (i * N + j)) | (1u << (j * N + i));
                 if (fmaf(d0x, d0x, d0y * d0y) <= S.wide2) {
@@ -369,7 +404,7 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
                 }
             }
         const unsigned long long self = lj_sweep_pair<true>(S, 0.0f, 0.0f);
-        *g.mask(total, PW) = self;
+        *g.mask(PW) = self;
         cands += N * __popcll(self);
         if (self)
             for (int i = 0; i < N; ++i) nonempty |= 1u << (i * N + i);
@@ -398,7 +433,7 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
                     nonempty &= nonempty - 1u;
                     i = N == 4 ? w >> 2 : (N == 2 ? w >> 1 : (N == 1 ? w : w / N));
                     j = w - i * N;
-                    bits = lj_image_mask(g, N, total, i, j);
+                    bits = lj_image_mask(g, N, i, j);
                 }
                 qb = __ffsll((long long)bits) - 1;
                 bits &= bits - 1;
@@ -422,14 +457,15 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
                 const double yb = fy * G.ld(1);
                 const double X = fx * G.ld(0) + yb * G.ld(2), Y = yb * G.ld(3);
                 const double cxi = G.ld(4 + ei * 4 + 2), cyi = G.ld(4 + ei * 4 + 3);
-                const int bi = G.comp0 + ei * n * 2, bj = G.comp0 + ej * n * 2;
+                const LjImage Ii = lj_image(P, G, n, ei), Ij = lj_image(P, G, n, ej);
+                const int bi = Ii.e0, bj = Ij.e0;
                 do {  // the surviving site pairs in iproduct order (lj_shape.rs:35-39), LJ2::energy in f64
                     const int p = __ffs((int)m) - 1;
                     m &= m - 1;
                     const int k = (p * (n == 3 ? 86 : (n == 4 ? 64 : (n == 2 ? 128 : 256)))) >> 8;  // p / n
                     const int l = p - k * n;
-                    const double sx = G.ld(bi + k * 2 + 0) + cxi, sy = G.ld(bi + k * 2 + 1) + cyi;
-                    const double ox = G.ld(bj + l * 2 + 0) + X, oy = G.ld(bj + l * 2 + 1) + Y;
+                    const double sx = lj_flip(G.ld(bi + k * 2 + 0), Ii.sx) + cxi, sy = lj_flip(G.ld(bi + k * 2 + 1), Ii.sy) + cyi;
+                    const double ox = lj_flip(G.ld(bj + l * 2 + 0), Ij.sx) + X, oy = lj_flip(G.ld(bj + l * 2 + 1), Ij.sy) + Y;
                     const double *pk = P.items[k];
                     e += lj_pair(sx - ox, sy - oy, pk[2], pk[3], pk[4], P.lj_shift[k]);
                 } while (m);

@@ -638,9 +638,10 @@ __host__ __device__ inline size_t thread_block_shared_bytes(const KProblem &P) {
 // (optimisation.rs:80-180) for every stage, seeds and bounds per stage as analyse_state /
 // generate_basis set them.  The replica's state lives in registers; the warp meets in t_lj_score.
 // Register budget = minimum resident blocks per SM (hard shapes: 14 warps per SM hold all 2,048
-// warps of a 65,536-replica batch at once).
-constexpr int thread_min_blocks(int kind, int ni) {
-    return kind == CP_LJ ? 14 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ni <= 11 ? 10 : 8)));
+// warps of a 65,536-replica batch at once; the budgets per component count and multiplicity are the
+// measured optima of the C5 sweep, tools/c5_sweep.py).
+constexpr int thread_min_blocks(int kind, int ni, int ns = 0) {
+    return kind == CP_LJ ? 14 : (ni == 0 ? 8 : (ni <= 6 ? 14 : (ns == 4 ? (ni <= 9 ? 14 : (ni <= 11 ? 12 : 8)) : (ni <= 11 ? 10 : 8))));
 }
 // proposals a lane may draw per pass before the warp goes on to score what it has: the draw loop
 // is divergent (lanes leave it as they find a proposal worth scoring), so its tail is cut
@@ -892,7 +893,7 @@ __device__ __noinline__ void t_loop_end(const KParams &K, double *mine, int e_do
 // Register budget = minimum resident blocks per SM: 14 warps per SM hold all 2,048 warps of a
 // 65,536-replica batch at once.
 template <int KIND, int NI, int NS, int RNG>
-__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI))
+__global__ void __launch_bounds__(kThreadBlock, thread_min_blocks(KIND, NI, NS))
 mc_thread_kernel(const __grid_constant__ KParams K) {
     static_assert(KIND != CP_LJ, "hard shapes");
     extern __shared__ double smem[];

@@ -227,6 +227,7 @@ struct TCands {
     int remaining = 0;
     int tune = 0;
     int first = -1;                     // (word << 6) | bit of the candidate to draw first; -1: none
+    unsigned long long skip = 0;        // bit of `first` when it is a self image: shape 0's pass over the self word leaves it out
     __device__ __forceinline__ void st(int w, unsigned long long x) {
         if constexpr (kRegs) {
             if (w == 0) r0 = x; else r1 = x;
@@ -298,7 +299,16 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
         if (q >= 0) first = (PW << 6) | q;
         c.st(PW, self);
         count += __popcll(self) * L.N;
+        // the nearest candidate is drawn first and must not be drawn again: a pair word gives its bit
+        // up here; the self word keeps it (shapes 1 .. N - 1 need it) and shape 0's pass skips it
         c.first = first;
+        c.skip = 0ull;
+        if (first >= 0) {
+            const int w = first >> 6;
+            const unsigned long long bit = 1ull << (first & 63);
+            if (w < PW) c.st(w, c.ld(w) & ~bit);
+            else c.skip = bit;
+        }
     } else {
         // a rolled loop over the pair words: a single copy of the 48-offset sweep in the kernel
 #pragma unroll 1
@@ -314,6 +324,7 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
         c.st(PW, self);
         count += __popcll(self) * L.N;
         c.first = -1;
+        c.skip = 0ull;
     }
     c.cur = 0;
     c.phase = -1;
@@ -325,20 +336,17 @@ __device__ __forceinline__ void t_sweep(const KProblem &P, const TView &v, const
 template <int NS>
 __device__ __forceinline__ void t_pop(TCands<NS> &c, int P, int N, int &ij, int &q) {
     constexpr bool kNearestFirst = NS == 0 || NS > 2;
-    if (kNearestFirst && c.first >= 0 && c.phase < 0) {
+    if (kNearestFirst && c.first >= 0) {
         const int w = c.first >> 6;
         q = c.first & 63;
         ij = w < P ? pair_of_word(w, N) : 0;  // a self image: the one of shape 0
-        c.phase = 0;
-        c.cur = c.ld(0);
-        if (w == 0) c.cur &= ~(1ull << q);
+        c.first = -1;
         return;
     }
     while (c.cur == 0ull) {
         ++c.phase;
-        const int w = c.phase < P ? c.phase : P;
-        c.cur = c.ld(w);
-        if (kNearestFirst && c.first >= 0 && c.phase == (c.first >> 6)) c.cur &= ~(1ull << (c.first & 63));
+        c.cur = c.ld(c.phase < P ? c.phase : P);
+        if (kNearestFirst && c.phase == P) c.cur &= ~c.skip;
     }
     q = __ffsll((long long)c.cur) - 1;
     c.cur &= c.cur - 1;

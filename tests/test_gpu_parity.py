@@ -486,6 +486,48 @@ def test_custom_group_three_operators_hexagonal(eng):
         eng.set_lanes(0)
 
 
+@pytest.mark.parametrize("ops,family", [
+    (["-x+1/2,y+1/2", "x,y", "x+1/2,-y+1/2", "-x,-y"], "Orthorhombic"),   # p2gg, reordered: operator 0 is a glide
+    (["-x,-y", "x,y"], "Monoclinic"),                                      # p2 with the two-fold axis first
+    (["x,y", "-x,-y", "y,-x", "-y,x"], "Orthorhombic"),                    # a four-fold axis: NOT row-sign related
+])
+def test_custom_groups_signed_and_unsigned_images(eng, ops, family):
+    """The multiplicity-4 builds and the LJ kernel store the rotated points of image 0 only when every
+    operator's rotation part is operator 0's with the signs of its rows flipped (KProblem::
+    signed_images), whatever operator 0 is; a group with a four-fold axis is not of that kind and
+    keeps the points of every image.  Scores and trajectories against the oracle, hard shapes and LJ."""
+    fam = {"Monoclinic": orc.MONOCLINIC, "Orthorhombic": orc.ORTHORHOMBIC}[family]
+    for spec in (("polygon", 5), ("trimer",), ("lj_trimer",)):
+        cshape, oshape = __import__("common").make_shapes(spec)
+        ostate = orc.state_from_group(oshape, "p1", orc.MATH_CP)
+        ostate.family, ostate.n_syms = fam, len(ops)
+        mats = []
+        for i, o in enumerate(ops):
+            assert orc.lib().orc_transform_from_operations(o.encode(), C.byref(ostate.syms[i])) == 0
+            r = ostate.syms[i].rows()
+            mats.append([r[0][0], r[1][0], r[2][0], r[0][1], r[1][1], r[2][1], r[0][2], r[1][2], r[2][2]])
+        radius = orc.lib().orc_shape_enclosing_radius(oshape[0], oshape[1], len(oshape[1]))
+        angle = math.pi / 2
+        dof = [4.0 * radius * len(ops), 1.0, angle, -0.5 + 0.5 / len(ops), -0.5 + 0.5 / len(ops), 0.0]
+        orc.set_dof(ostate, dof)
+        group = cp.api.group_from_symmetries("custom", family, mats)
+        cls = cp.PotentialState if spec[0].startswith("lj") else cp.PackedState
+        cstate = cls.from_group(cshape, group)
+        cstate.dof = dof
+        dofs = [dof] + random_dofs(ostate, 150, seed=17)
+        ref = oracle_scores(ostate, dofs)
+        got = eng.score(cstate._problem, dofs)
+        assert all(same_float(a, b) for a, b in zip(got, ref)), (spec, ops)
+        assert any(math.isnan(v) for v in ref) or spec[0].startswith("lj")  # overlapping states are in the sample
+        sched = cp.MCOptimiser(0.05, 0.5, 0.01, 900, 300, 0, None).schedule
+        _, res = eng.run(cstate._problem, [sched], 16, rng=cp.RNG_PCG64MCG)
+        for k in range(16):
+            s = orc.clone(ostate)
+            rc, _, rej = orc.optimise(s, 0.05, 0.5, 0.01, 900, 300, k)
+            assert rc == 0 and list(res[k].dof) == orc.get_dof(s) and res[k].rejections == rej, (spec, ops, k)
+            assert res[k].score == orc.score(s)
+
+
 def test_large_replica_ids_and_seed_base(eng):
     """Seeds are 64-bit: replica ids beyond 2^32 and a seed_base offset reproduce the oracle's
     seed_from_u64(seed_base + id) streams."""

@@ -198,7 +198,10 @@ cp_status cp_run(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stag
  *    work on OTHER streams that reads them (a collective on the communicator's stream, a peer copy)
  *    must be ordered before the next cp_launch by the caller (event or stream wait).
  *  - the addresses returned by cp_device_buffers go stale when a cp_prepare with more replicas than
- *    any before it reallocates the result buffer; ask again after every cp_prepare. */
+ *    any before it reallocates the result buffer; ask again after every cp_prepare.
+ * Tuning knobs read from the environment by cp_prepare (measurement only; results never depend on
+ * them): CP_WARP_FILL = replicas per warp of the one-thread-per-replica kernels (default: chosen at
+ * the launch from the occupancy), CP_DRAW_CAP = proposals a lane may draw per pass (default 3). */
 cp_status cp_prepare(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *stages,
                      int n_stages, int rng_mode, uint64_t seed_base, uint64_t replica_begin,
                      uint64_t n_replicas, const double *init_dof);

@@ -310,13 +310,17 @@ __device__ __forceinline__ unsigned lj_prefilter(const KProblem &P, Geo g, int N
     const float d0y = (float)(g.ld(4 + j * 4 + 3) - g.ld(4 + i * 4 + 3));
     const int cix = (qb * 37) >> 8;
     const float fix = (float)(cix - 3), fiy = (float)(qb - cix * 7 - 3);
-    const float Dx = fmaf(fix, p0.x, fmaf(fiy, p0.y, d0x)), Dy = fmaf(fiy, p1.x, d0y);
+    // Evaluated in shape i's frame with its row signs undone (a sign flip of one coordinate of
+    // everything leaves every squared distance as it is, bit for bit): A's sites as stored, B's with
+    // the product of the two sign pairs, the displacement with i's.
+    const float Dx = lj_flipf(fmaf(fix, p0.x, fmaf(fiy, p0.y, d0x)), Ii.sx), Dy = lj_flipf(fmaf(fiy, p1.x, d0y), Ii.sy);
+    const unsigned bsx = Ii.sx ^ Ij.sx, bsy = Ii.sy ^ Ij.sy;
     float bx[NN], by[NN];
 #pragma unroll
     for (int l = 0; l < NN; ++l) {
         const float2 B = g.ldf(cj + (l < n ? l : 0));
-        bx[l] = lj_flipf(B.x, Ij.sx) + Dx;
-        by[l] = lj_flipf(B.y, Ij.sy) + Dy;
+        bx[l] = lj_flipf(B.x, bsx) + Dx;
+        by[l] = lj_flipf(B.y, bsy) + Dy;
     }
     unsigned m = 0u;
 #pragma unroll
@@ -325,8 +329,7 @@ __device__ __forceinline__ unsigned lj_prefilter(const KProblem &P, Geo g, int N
         const double cut = P.items[k < n ? k : 0][4];
         const float c = (float)cut * (1.0f + 1e-6f) + 2.0f * p1.y;
         const float lim = cut == cut ? c * c * (1.0f + 1e-6f) : 3.0e38f;
-        const float2 A0 = g.ldf(ci + (k < n ? k : 0));
-        const float2 A = make_float2(lj_flipf(A0.x, Ii.sx), lj_flipf(A0.y, Ii.sy));
+        const float2 A = g.ldf(ci + (k < n ? k : 0));
 #pragma unroll
         for (int l = 0; l < NN; ++l) {
             const float dx = A.x - bx[l], dy = A.y - by[l];
@@ -455,17 +458,20 @@ __device__ __forceinline__ double t_lj_score_pooled(const KProblem &P, TGeo g, c
                 const double dix = (double)(cix - 3), diy = (double)(qb - cix * 7 - 3);
                 const double fx = G.ld(4 + ej * 4 + 0) + dix, fy = G.ld(4 + ej * 4 + 1) + diy;
                 const double yb = fy * G.ld(1);
-                const double X = fx * G.ld(0) + yb * G.ld(2), Y = yb * G.ld(3);
-                const double cxi = G.ld(4 + ei * 4 + 2), cyi = G.ld(4 + ei * 4 + 3);
                 const LjImage Ii = lj_image(P, G, n, ei), Ij = lj_image(P, G, n, ej);
+                // in shape i's frame with its row signs undone: the differences below come out with
+                // i's signs, exactly (negation commutes with rounding), and LJ2::energy squares them
+                const double X = lj_flip(fx * G.ld(0) + yb * G.ld(2), Ii.sx), Y = lj_flip(yb * G.ld(3), Ii.sy);
+                const double cxi = lj_flip(G.ld(4 + ei * 4 + 2), Ii.sx), cyi = lj_flip(G.ld(4 + ei * 4 + 3), Ii.sy);
+                const unsigned bsx = Ii.sx ^ Ij.sx, bsy = Ii.sy ^ Ij.sy;
                 const int bi = Ii.e0, bj = Ij.e0;
                 do {  // the surviving site pairs in iproduct order (lj_shape.rs:35-39), LJ2::energy in f64
                     const int p = __ffs((int)m) - 1;
                     m &= m - 1;
                     const int k = (p * (n == 3 ? 86 : (n == 4 ? 64 : (n == 2 ? 128 : 256)))) >> 8;  // p / n
                     const int l = p - k * n;
-                    const double sx = lj_flip(G.ld(bi + k * 2 + 0), Ii.sx) + cxi, sy = lj_flip(G.ld(bi + k * 2 + 1), Ii.sy) + cyi;
-                    const double ox = lj_flip(G.ld(bj + l * 2 + 0), Ij.sx) + X, oy = lj_flip(G.ld(bj + l * 2 + 1), Ij.sy) + Y;
+                    const double sx = G.ld(bi + k * 2 + 0) + cxi, sy = G.ld(bi + k * 2 + 1) + cyi;
+                    const double ox = lj_flip(G.ld(bj + l * 2 + 0), bsx) + X, oy = lj_flip(G.ld(bj + l * 2 + 1), bsy) + Y;
                     const double *pk = P.items[k];
                     e += lj_pair(sx - ox, sy - oy, pk[2], pk[3], pk[4], P.lj_shift[k]);
                 } while (m);

@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--config-steps", type=int, default=2, help="timed passes of each extra configuration")
     ap.add_argument("--c5-total", type=int, default=8388608, help="replicas of the C5 sweep (rounded down to 70 equal cells)")
     ap.add_argument("--c5-mc-steps", type=int, default=1000)
+    ap.add_argument("--c5-granularity", type=int, default=6,
+                    help="C5 cells costing more than 1/granularity of a rank's share are cut into chunks below that")
     ap.add_argument("--c5-streams", type=int, default=2, choices=[1, 2],
                     help="contexts per GPU the C5 chunks alternate over (2: cell tails overlap)")
     return ap.parse_args()
@@ -398,7 +400,7 @@ def run_c5(B):
     mpr = schedule_moves(schedules)
     states = [cp.PackedState.from_group(cp.LineShape.polygon(n), g) for n, g in cells]
     est = [cpd.estimated_cell_cost(n, st.total_shapes()) for (n, g), st in zip(cells, states)]
-    chunks = cpd.sweep_chunks(est, per_cell, B.world)
+    chunks = cpd.sweep_chunks(est, per_cell, B.world, granularity=args.c5_granularity)
     best_dev = B.best_view()
     slots = len(chunks)  # a rank never holds more chunks than there are
     nan_rec = torch.frombuffer(bytearray(cpd.pack_best([0.0] * 6, float("nan"), 0, 0, 2 ** 64 - 1)), dtype=torch.uint8)

@@ -8,9 +8,11 @@
 //     draw, and for hard shapes a cell move that the Metropolis rule rejects even if valid is
 //     rejected there too, before any overlap test (the packing fraction depends on the cell only);
 //   * phase A, per lane: positions of the symmetry images in f64 (reference expressions), the
-//     rotated shape points in f32, and the exactly pruned sweep over the periodic images of HALF of
-//     the ordered shape pairs (the reference tests (i, j, t) and its mirror image (j, i, -t); one
-//     certificate covers both, cp_filter.h); candidates become bits of one 64-bit word per pair;
+//     rotated shape points in f32 (of image 0 only where the others are its row-sign flips, see
+//     TLayout), and the single-precision sweep over the periodic images of HALF of the ordered shape
+//     pairs - a proven superset of the images the reference's f64 filter keeps (the reference tests
+//     (i, j, t) and its mirror image (j, i, -t); one certificate covers both, cp_filter.h);
+//     candidates become bits of one 64-bit word per pair;
 //   * phase B, whole warp: the candidates of all 32 replicas are drawn in rounds into a shared pool
 //     of 32 entries, one entry per lane.  A lane evaluates the f32 CERTIFICATE of its entry
 //     (cp_filter.h): "every component test is false" / "some component test is true", proven about
@@ -18,6 +20,8 @@
 //     evaluated with the reference's own f64 expressions (both mirror sides, each behind the
 //     reference's own distance filter), one pair per lane.  Replicas drop out at their first hit;
 //   * phase C, per lane: the decision.
+// A warp holds up to 32 replicas; how many is chosen at the launch (KParams::warp_fill,
+// cp_thread_inst.cuh).
 // So every decision is the reference's: certificates only ever replace f64 evaluations whose result
 // they prove.  Arithmetic of everything that reaches a decision: reference expression order, f64,
 // no contraction (-fmad=false).

@@ -27,6 +27,15 @@ struct Pts {
     float r(int k) const { return pr[k]; }
 };
 
+// the same points with the row signs of an image applied (the kernel's TPtsSigned)
+struct PtsSigned {
+    const float *px, *py, *pr;
+    float sx, sy;
+    float x(int k) const { return sx * px[k]; }
+    float y(int k) const { return sy * py[k]; }
+    float r(int k) const { return pr[k]; }
+};
+
 static double wrap_unit(double v) {
     double t = v - (-0.5);
     t = t - std::trunc(t);
@@ -40,6 +49,7 @@ struct Stats {
     unsigned long long exact_moves = 0, overlap_moves = 0, exact_cands = 0, max_cands = 0;
     unsigned long long hist[16] = {};
     unsigned long long errors = 0;
+    unsigned long long signed_checked = 0;
 };
 
 struct Cand {
@@ -49,7 +59,8 @@ struct Cand {
     double X, Y;      // image position of j (f64, reference expressions)
 };
 
-static float run_filter(int kind, int n, bool chain, const Pts &A, const Pts &B, float dX, float dY, float tau,
+template <class PA, class PB>
+static float run_filter(int kind, int n, bool chain, const PA &A, const PB &B, float dX, float dY, float tau,
                         unsigned (&amb)[CPF_MAX_WORDS]) {
     for (unsigned &w : amb) w = 0u;
 #define CHAIN_CASE(NN)                                                   \
@@ -129,6 +140,23 @@ static int filtered_check(const orc_state *s, bool chain, Stats &st) {
                 vr[k][q] = (float)it.c;
             }
         }
+    }
+    // signed images (cp_api.cu: make_kproblem): every rotation part = operator 0's with row signs
+    bool signed_images = true;
+    float sgn[8][2];
+    for (int k = 0; k < N; ++k) {
+        const double (*S)[3] = s->syms[k].m, (*S0)[3] = s->syms[0].m;
+        bool found = false;
+        for (int q = 0; q < 4 && !found; ++q) {
+            const float ax = (q & 1) ? -1.0f : 1.0f, ay = (q & 2) ? -1.0f : 1.0f;
+            if ((float)S[0][0] == ax * (float)S0[0][0] && (float)S[0][1] == ax * (float)S0[0][1] &&
+                (float)S[1][0] == ay * (float)S0[1][0] && (float)S[1][1] == ay * (float)S0[1][1]) {
+                sgn[k][0] = ax;
+                sgn[k][1] = ay;
+                found = true;
+            }
+        }
+        if (!found) signed_images = false;
     }
     // candidate list exactly as the kernel builds it (cp_thread.cuh: t_sweep): the single-precision
     // sweep over half of the ordered pairs; `band` = the certificate's evaluation site cannot be sure
@@ -245,6 +273,26 @@ static int filtered_check(const orc_state *s, bool chain, Stats &st) {
         unsigned amb[CPF_MAX_WORDS];
         const float cmin = run_filter(kind, n, chain, A, B, dX, dY, tau, amb);
         st.evals++;
+        if (signed_images) {
+            // the multiplicity-4 builds evaluate the certificate from image 0's points alone, in shape
+            // i's frame with its row signs undone (cp_thread.cuh: t_overlap_warp): same cmin, same
+            // tau, same ambiguous set, bit for bit
+            const float sAx = sgn[C.i][0], sAy = sgn[C.i][1];
+            Pts A0{vx[0], vy[0], vr[0]};
+            PtsSigned B0{vx[0], vy[0], vr[0], sAx * sgn[C.j][0], sAy * sgn[C.j][1]};
+            const float dX2 = dX * sAx, dY2 = dY * sAy;
+            const float tau2 = kind == ORC_POLYGON ? cpf_tau(Rf, dX2, dY2) : cpf_tau_discs(Rf, dX2, dY2);
+            unsigned amb2[CPF_MAX_WORDS];
+            const float cmin2 = run_filter(kind, n, chain, A0, B0, dX2, dY2, tau2, amb2);
+            bool same = std::memcmp(&cmin, &cmin2, sizeof cmin) == 0 && std::memcmp(&tau, &tau2, sizeof tau) == 0;
+            for (int w = 0; w < CPF_MAX_WORDS; ++w) same = same && amb[w] == amb2[w];
+            if (!same) {
+                st.errors++;
+                std::fprintf(stderr, "signed-image certificate differs: pair (%d,%d) cmin %a vs %a tau %a vs %a\n", C.i, C.j,
+                             cmin, cmin2, tau, tau2);
+            }
+            st.signed_checked++;
+        }
         bool candA, candB = false;
         exact_side(C.i, C.j, C.ix, C.iy, C.incell, &candA, tA);
         if (!C.incell) exact_side(C.j, C.i, -C.ix, -C.iy, false, &candB, tB);
@@ -425,11 +473,11 @@ int main(int argc, char **argv) {
     std::printf("{\"shape\": \"%s\", \"sides\": %d, \"group\": \"%s\", \"replicas\": %d, \"moves\": %llu, \"in_bounds\": %llu, "
                 "\"scored\": %llu, \"cands_per_scored\": %.3f, \"max_cands\": %llu, \"evals_per_scored\": %.3f, "
                 "\"clear\": %llu, \"hit\": %llu, \"ambiguous\": %llu, \"band\": %llu, \"exact_moves_frac\": %.5f, "
-                "\"exact_cands_per_scored\": %.5f, \"overlap_frac\": %.4f, \"errors\": %llu}\n",
+                "\"exact_cands_per_scored\": %.5f, \"overlap_frac\": %.4f, \"signed_checked\": %llu, \"errors\": %llu}\n",
                 shape, sides, group, replicas, moves, inb, st.scored, (double)st.cands / st.scored, st.max_cands,
                 (double)st.evals / st.scored, st.clear, st.hit, st.ambiguous, st.band,
                 (double)st.exact_moves / st.scored, (double)st.exact_cands / st.scored,
-                (double)st.overlap_moves / st.scored, st.errors);
+                (double)st.overlap_moves / st.scored, st.signed_checked, st.errors);
     std::printf("cands histogram:");
     for (int i = 0; i < 16; ++i) std::printf(" %llu", st.hist[i]);
     std::printf("\n");

@@ -8,7 +8,9 @@ trajectories of the oracle, checks at every scored proposal that
     expressions, on both mirror sides (line2.rs:29-54, atom2.rs:21-26);
   * every certified hit is a true shape test of a candidate the reference does test;
   * the verdict assembled the way the kernel assembles it equals check_intersection
-    (packed.rs:127-167).
+    (packed.rs:127-167);
+  * the certificate evaluated from image 0's points alone (row signs, shape i's frame - what the
+    multiplicity-4 builds do) has the same cmin, tau and ambiguous set, bit for bit.
 No GPU involved: this is the proof obligation of the certificates exercised on the host.
 """
 import json
@@ -61,6 +63,9 @@ def test_certificates_are_sound(checker, shape, sides, group, replicas, steps, e
     stats = json.loads(out.stdout.splitlines()[0])
     assert stats["errors"] == 0
     assert stats["scored"] > 1000 and stats["clear"] + stats["hit"] > 0
+    # every built-in group is a signed-image group: each certificate was also evaluated the way the
+    # multiplicity-4 builds do (image 0's points, row signs, shape i's frame) and gave the same bits
+    assert stats["signed_checked"] >= stats["clear"] + stats["hit"] + stats["ambiguous"]
     # the certificates decide most shape pairs; the f64 path is the exception
     assert stats["ambiguous"] < 0.5 * (stats["clear"] + stats["hit"] + stats["ambiguous"])
 

@@ -351,8 +351,6 @@ cp_status cp_prepare(cp_ctx *ctx, const cp_problem *problem, const cp_schedule *
     K.replica_begin = replica_begin;
     K.n_replicas = n_replicas;
     K.draw_cap = 3;
-    K.tune = 0;
-    if (const char *e = std::getenv("CP_TUNE")) K.tune = std::atoi(e);
     K.warp_fill = 0;  // 0: chosen at the launch from the occupancy (cp_thread_inst.cuh)
     if (const char *e = std::getenv("CP_WARP_FILL")) K.warp_fill = std::atoi(e);  // tuning knob
     if (const char *e = std::getenv("CP_DRAW_CAP")) {  // tuning knob, see cp_thread.cuh

@@ -65,7 +65,6 @@ struct KParams {
     cp_replica_result *out;
     int *error_flag;
     int draw_cap;  // thread kernels: proposals a lane may draw per pass (cp_thread.cuh)
-    int tune;      // experiment switches (CP_TUNE)
     int warp_fill; // thread kernels: replicas per warp (<= 32; cp_thread_inst.cuh: thread_mc_launch)
 };
 

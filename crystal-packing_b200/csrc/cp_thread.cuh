@@ -229,7 +229,6 @@ struct TCands {
     unsigned long long cur = 0;         // bits of the current word still to draw
     int phase = -1;                     // words: 0 .. P - 1 the pairs i < j, P .. P + N - 1 the self word once per shape
     int remaining = 0;
-    int tune = 0;
     int first = -1;                     // (word << 6) | bit of the candidate to draw first; -1: none
     unsigned long long skip = 0;        // bit of `first` when it is a self image: shape 0's pass over the self word leaves it out
     __device__ __forceinline__ void st(int w, unsigned long long x) {
@@ -944,7 +943,6 @@ mc_thread_kernel(const __grid_constant__ KParams K) {
     h.done = !active;
     TCands<NS> cands;
     cands.sh = v.masks + threadIdx.x;
-    cands.tune = K.tune;
     // Every lane walks its own (stage, outer loop, inner step) schedule: replicas of one warp need
     // different numbers of scored proposals per inner loop, and synchronising at loop ends would
     // leave the faster lanes idle there.  Only the score phases below are warp-wide.
